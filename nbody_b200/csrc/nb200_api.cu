@@ -1,0 +1,1070 @@
+// nb200 -- implementation of the C ABI declared in include/nb200.h.
+//
+// Host-side structure (one context = the devices of one process):
+//   lanes    one per entry of the device list; each has its own stream and
+//            holds one body shard of every state vector
+//   buffers  per-lane cudaMalloc allocations behind an opaque handle
+//   ops      loop over lanes, launch asynchronously on the lane's stream
+// The reference does the same work with one OpenMP host thread per device and
+// fully replicated buffers (nbody/nbody_engine_cuda.cpp:226-241,
+// nbody_engine_cuda_memory.cpp:4-36); here launches are asynchronous, so one
+// host thread is enough, and state stays sharded.
+#include <stdarg.h>
+#include <algorithm>
+
+#include "nb200_common.cuh"
+#include "nb200_comm.cuh"
+#include "nb200_direct.cuh"
+#include "nb200_stateops.cuh"
+#include "nb200_bh.cuh"
+
+#define NB200_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+int fail(nb200_ctx* ctx, int status, const char* fmt, ...)
+{
+	char	text[512];
+	va_list	ap;
+	va_start(ap, fmt);
+	vsnprintf(text, sizeof(text), fmt, ap);
+	va_end(ap);
+	if(ctx != nullptr)
+	{
+		ctx->err = text;
+	}
+	return status;
+}
+
+#define CU(ctx, call)                                                                                  \
+	do                                                                                                 \
+	{                                                                                                  \
+		cudaError_t cu_res_ = (call);                                                                  \
+		if(cu_res_ != cudaSuccess)                                                                     \
+		{                                                                                              \
+			return fail(ctx, NB200_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                \
+						cudaGetErrorString(cu_res_));                                                  \
+		}                                                                                              \
+	} while(0)
+
+#define NC(ctx, call)                                                                                  \
+	do                                                                                                 \
+	{                                                                                                  \
+		ncclResult_t nc_res_ = (call);                                                                 \
+		if(nc_res_ != ncclSuccess)                                                                     \
+		{                                                                                              \
+			return fail(ctx, NB200_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call,                \
+						ctx->nccl->GetErrorString(nc_res_));                                           \
+		}                                                                                              \
+	} while(0)
+
+#define LAUNCHED(ctx)                                                                                  \
+	do                                                                                                 \
+	{                                                                                                  \
+		++(ctx)->launches;                                                                             \
+		CU(ctx, cudaGetLastError());                                                                   \
+	} while(0)
+
+bool valid(const nb200_ctx* ctx, const nb200_buf* b)
+{
+	return ctx != nullptr && b != nullptr && ctx->live.count(b) != 0;
+}
+
+unsigned ew_grid(const nb200_lane& lane, size_t count)
+{
+	size_t	nvec = (count + NB200_VEC - 1) / NB200_VEC;
+	size_t	blocks = (nvec + NB200_EW_THREADS - 1) / NB200_EW_THREADS;
+	size_t	cap = static_cast<size_t>(lane.sm_count) * 8;	// 8 x 256 threads = full occupancy
+	return static_cast<unsigned>(std::max<size_t>(1, std::min(blocks, cap)));
+}
+
+real* lane_ptr(const nb200_buf* b, size_t lane)
+{
+	return static_cast<real*>(b->dptr[lane]);
+}
+
+void free_lane(nb200_lane& l)
+{
+	cudaSetDevice(l.dev);
+	bh_free(l.bh);
+	l.bh = nullptr;
+	if(l.mass) { cudaFree(l.mass); }
+	if(l.src) { cudaFree(l.src); }
+	if(l.partial) { cudaFree(l.partial); }
+	if(l.d_scalar) { cudaFree(l.d_scalar); }
+	if(l.h_scalar) { cudaFreeHost(l.h_scalar); }
+	l.mass = nullptr;
+	l.src = nullptr;
+	l.partial = nullptr;
+	l.d_scalar = nullptr;
+	l.h_scalar = nullptr;
+}
+
+// Make every lane's `src` hold the packed bodies of all shards.
+// lanes > 1: peer copies between this process's lanes; nranks > 1: NCCL all-gather.
+int gather_sources(nb200_ctx* ctx)
+{
+	const size_t	shard_bytes = ctx->n_shard * sizeof(body4);
+	if(ctx->nranks > 1)
+	{
+		nb200_lane&	l = ctx->lanes[0];
+		body4*		mine = l.src + static_cast<size_t>(l.shard) * ctx->n_shard;
+		NC(ctx, ctx->nccl->AllGather(mine, l.src, ctx->n_shard * 4, NB200_NCCL_REAL,
+									 static_cast<ncclComm_t>(ctx->comm), l.stream));
+		return NB200_OK;
+	}
+	if(ctx->lanes.size() > 1)
+	{
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			CU(ctx, cudaEventRecord(l.ev_packed, l.stream));
+		}
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			for(auto& p : ctx->lanes)
+			{
+				if(&p == &l) { continue; }
+				CU(ctx, cudaStreamWaitEvent(l.stream, p.ev_packed, 0));
+				size_t off = static_cast<size_t>(p.shard) * ctx->n_shard;
+				CU(ctx, cudaMemcpyPeerAsync(l.src + off, l.dev, p.src + off, p.dev, shard_bytes, l.stream));
+			}
+			CU(ctx, cudaEventRecord(l.ev_gathered, l.stream));
+		}
+		// A lane may not repack (next fcompute) before every peer has read its shard.
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			for(auto& p : ctx->lanes)
+			{
+				if(&p != &l) { CU(ctx, cudaStreamWaitEvent(l.stream, p.ev_gathered, 0)); }
+			}
+		}
+	}
+	return NB200_OK;
+}
+
+int check_state_pair(nb200_ctx* ctx, const nb200_buf* y, const nb200_buf* f, const char* who)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "%s: y is not a buffer of this context", who); }
+	if(!valid(ctx, f)) { return fail(ctx, NB200_ERR_ARG, "%s: f is not a buffer of this context", who); }
+	if(ctx->n == 0) { return fail(ctx, NB200_ERR_STATE, "%s: nb200_set_bodies has not been called", who); }
+	if(!y->sharded || !f->sharded)
+	{
+		return fail(ctx, NB200_ERR_ARG, "%s: y and f must be state vectors of 6*N elements", who);
+	}
+	return NB200_OK;
+}
+
+int pack_and_gather(nb200_ctx* ctx, const nb200_buf* y)
+{
+	for(size_t li = 0; li < ctx->lanes.size(); ++li)
+	{
+		nb200_lane& l = ctx->lanes[li];
+		CU(ctx, cudaSetDevice(l.dev));
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[0], l.stream)); }
+		unsigned grid = static_cast<unsigned>((ctx->n_shard + 255) / 256);
+		direct_pack<<<grid, 256, 0, l.stream>>>(lane_ptr(y, li), l.mass, l.src, ctx->n_shard,
+												static_cast<size_t>(l.shard) * ctx->n_shard);
+		LAUNCHED(ctx);
+	}
+	int rc = gather_sources(ctx);
+	if(rc != NB200_OK) { return rc; }
+	if(ctx->opt_timing)
+	{
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			CU(ctx, cudaEventRecord(l.ev_t[1], l.stream));
+		}
+	}
+	return NB200_OK;
+}
+
+template<int IPT>
+void launch_pairs(nb200_ctx* ctx, nb200_lane& l, const real* y, real* out, dim3 grid, int n_tiles, int tiles_per_seg, int write_f)
+{
+	direct_pairs<IPT><<<grid, NB200_DIRECT_THREADS, 0, l.stream>>>(
+		l.src, y, out, ctx->n_shard, static_cast<size_t>(l.shard) * ctx->n_shard, n_tiles, tiles_per_seg, write_f);
+}
+
+}  // namespace
+
+// ---- library / device queries ------------------------------------------------
+NB200_API int nb200_real_size(void)
+{
+	return static_cast<int>(sizeof(real));
+}
+
+NB200_API int nb200_device_count(int* count)
+{
+	if(count == nullptr) { return NB200_ERR_ARG; }
+	*count = 0;
+	cudaError_t res = cudaGetDeviceCount(count);
+	if(res != cudaSuccess)
+	{
+		*count = 0;
+		cudaGetLastError();
+		return NB200_ERR_CUDA;
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_comm_unique_id(void* uid128)
+{
+	if(uid128 == nullptr) { return NB200_ERR_ARG; }
+	std::string	err;
+	nccl_api*	api = nccl_load(err);
+	if(api == nullptr)
+	{
+		fprintf(stderr, "nb200: %s\n", err.c_str());
+		return NB200_ERR_NCCL;
+	}
+	static_assert(sizeof(ncclUniqueId) == NB200_UID_BYTES, "NCCL unique id size");
+	ncclUniqueId id;
+	if(api->GetUniqueId(&id) != ncclSuccess) { return NB200_ERR_NCCL; }
+	memcpy(uid128, &id, sizeof(id));
+	return NB200_OK;
+}
+
+// ---- context -------------------------------------------------------------------
+NB200_API int nb200_create(nb200_ctx** out, const int* dev_ids, int nlanes, int rank, int nranks, const void* uid128)
+{
+	if(out == nullptr) { return NB200_ERR_ARG; }
+	*out = nullptr;
+	if(dev_ids == nullptr || nlanes < 1 || nranks < 1 || rank < 0 || rank >= nranks) { return NB200_ERR_ARG; }
+	if(nlanes > 1 && nranks > 1)
+	{
+		fprintf(stderr, "nb200_create: use either several lanes in one process or one lane per rank\n");
+		return NB200_ERR_UNSUPPORTED;
+	}
+	if(nranks > 1 && uid128 == nullptr) { return NB200_ERR_ARG; }
+	int	count = 0;
+	if(cudaGetDeviceCount(&count) != cudaSuccess || count < 1)
+	{
+		cudaGetLastError();
+		fprintf(stderr, "nb200_create: no CUDA device (there is no CPU fallback)\n");
+		return NB200_ERR_CUDA;
+	}
+	for(int i = 0; i < nlanes; ++i)
+	{
+		if(dev_ids[i] < 0 || dev_ids[i] >= count)
+		{
+			fprintf(stderr, "nb200_create: invalid device id %d, must be in [0, %d)\n", dev_ids[i], count);
+			return NB200_ERR_ARG;
+		}
+	}
+	nb200_ctx* ctx = new nb200_ctx();
+	ctx->rank = rank;
+	ctx->nranks = nranks;
+	ctx->nshards = nlanes * nranks;
+	ctx->first_shard = (nranks > 1) ? rank : 0;
+	ctx->lanes.resize(static_cast<size_t>(nlanes));
+	int status = NB200_OK;
+	for(int i = 0; i < nlanes && status == NB200_OK; ++i)
+	{
+		nb200_lane& l = ctx->lanes[static_cast<size_t>(i)];
+		l.dev = dev_ids[i];
+		l.shard = ctx->first_shard + i;
+		cudaDeviceProp prop;
+		bool ok = cudaSetDevice(l.dev) == cudaSuccess &&
+				  cudaGetDeviceProperties(&prop, l.dev) == cudaSuccess &&
+				  cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
+				  cudaEventCreateWithFlags(&l.ev_packed, cudaEventDisableTiming) == cudaSuccess &&
+				  cudaEventCreateWithFlags(&l.ev_gathered, cudaEventDisableTiming) == cudaSuccess &&
+				  cudaMalloc(&l.d_scalar, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+				  cudaMallocHost(&l.h_scalar, 8 * sizeof(unsigned long long)) == cudaSuccess;
+		for(int e = 0; e < 5 && ok; ++e) { ok = cudaEventCreate(&l.ev_t[e]) == cudaSuccess; }
+		for(int e = 0; e < 8 && ok; ++e) { ok = cudaEventCreate(&l.ev_mark[e]) == cudaSuccess; }
+		if(!ok)
+		{
+			fprintf(stderr, "nb200_create: device %d setup failed: %s\n", l.dev, cudaGetErrorString(cudaGetLastError()));
+			status = NB200_ERR_CUDA;
+			break;
+		}
+		l.sm_count = prop.multiProcessorCount;
+		if(prop.major < 10)
+		{
+			fprintf(stderr, "nb200_create: device %d is sm_%d%d; this library is built for sm_100a only\n", l.dev, prop.major, prop.minor);
+			status = NB200_ERR_UNSUPPORTED;
+		}
+	}
+	if(status == NB200_OK && nlanes > 1)
+	{
+		// Peer access between distinct devices of the lane list (NVLink / NVSwitch).
+		for(auto& a : ctx->lanes)
+		{
+			for(auto& b : ctx->lanes)
+			{
+				if(a.dev == b.dev) { continue; }
+				int can = 0;
+				cudaDeviceCanAccessPeer(&can, a.dev, b.dev);
+				if(can)
+				{
+					cudaSetDevice(a.dev);
+					cudaError_t r = cudaDeviceEnablePeerAccess(b.dev, 0);
+					if(r != cudaSuccess && r != cudaErrorPeerAccessAlreadyEnabled) { status = NB200_ERR_CUDA; }
+					cudaGetLastError();
+				}
+			}
+		}
+	}
+	if(status == NB200_OK && nranks > 1)
+	{
+		ctx->nccl = nccl_load(ctx->err);
+		if(ctx->nccl == nullptr)
+		{
+			fprintf(stderr, "nb200_create: %s\n", ctx->err.c_str());
+			status = NB200_ERR_NCCL;
+		}
+		else
+		{
+			ncclUniqueId id;
+			memcpy(&id, uid128, sizeof(id));
+			ncclComm_t comm = nullptr;
+			cudaSetDevice(ctx->lanes[0].dev);
+			ncclResult_t r = ctx->nccl->CommInitRank(&comm, nranks, id, rank);
+			if(r != ncclSuccess)
+			{
+				fprintf(stderr, "nb200_create: ncclCommInitRank: %s\n", ctx->nccl->GetErrorString(r));
+				status = NB200_ERR_NCCL;
+			}
+			ctx->comm = comm;
+		}
+	}
+	if(status != NB200_OK)
+	{
+		nb200_destroy(ctx);
+		return status;
+	}
+	*out = ctx;
+	return NB200_OK;
+}
+
+NB200_API int nb200_destroy(nb200_ctx* ctx)
+{
+	if(ctx == nullptr) { return NB200_OK; }
+	for(auto& l : ctx->lanes)
+	{
+		cudaSetDevice(l.dev);
+		if(l.stream) { cudaStreamSynchronize(l.stream); }
+	}
+	if(ctx->comm != nullptr && ctx->nccl != nullptr)
+	{
+		ctx->nccl->CommDestroy(static_cast<ncclComm_t>(ctx->comm));
+	}
+	// Buffers the caller never released
+	std::vector<const nb200_buf*> leaked(ctx->live.begin(), ctx->live.end());
+	for(const nb200_buf* b : leaked) { nb200_free(ctx, const_cast<nb200_buf*>(b)); }
+	for(auto& l : ctx->lanes)
+	{
+		free_lane(l);
+		cudaSetDevice(l.dev);
+		if(l.ev_packed) { cudaEventDestroy(l.ev_packed); }
+		if(l.ev_gathered) { cudaEventDestroy(l.ev_gathered); }
+		for(auto& e : l.ev_t) { if(e) { cudaEventDestroy(e); } }
+		for(auto& e : l.ev_mark) { if(e) { cudaEventDestroy(e); } }
+		if(l.stream) { cudaStreamDestroy(l.stream); }
+	}
+	cudaGetLastError();
+	delete ctx;
+	return NB200_OK;
+}
+
+NB200_API const char* nb200_last_error(const nb200_ctx* ctx)
+{
+	return ctx != nullptr ? ctx->err.c_str() : "null context";
+}
+
+NB200_API int nb200_sync(nb200_ctx* ctx)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	for(auto& l : ctx->lanes)
+	{
+		CU(ctx, cudaSetDevice(l.dev));
+		CU(ctx, cudaStreamSynchronize(l.stream));
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_shards(const nb200_ctx* ctx, int* nshards, int* first_shard)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(nshards) { *nshards = ctx->nshards; }
+	if(first_shard) { *first_shard = ctx->first_shard; }
+	return NB200_OK;
+}
+
+NB200_API int nb200_describe(const nb200_ctx* ctx, char* text, size_t text_bytes)
+{
+	if(ctx == nullptr || text == nullptr || text_bytes == 0) { return NB200_ERR_ARG; }
+	std::string s;
+	char line[640];
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		cudaDeviceProp prop;
+		if(cudaGetDeviceProperties(&prop, ctx->lanes[i].dev) != cudaSuccess) { continue; }
+		snprintf(line, sizeof(line), "\t #%zu ID %d %s sm_%d%d SMs %d HBM %zu MB L2 %d KB shard %d/%d\n", i, ctx->lanes[i].dev,
+				 prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.totalGlobalMem >> 20, prop.l2CacheSize >> 10,
+				 ctx->lanes[i].shard, ctx->nshards);
+		s += line;
+	}
+	snprintf(line, sizeof(line), "\t precision %s, ranks %d, NCCL %s\n", sizeof(real) == 8 ? "FP64" : "FP32", ctx->nranks,
+			 ctx->comm ? "on" : "off");
+	s += line;
+	snprintf(text, text_bytes, "%s", s.c_str());
+	return NB200_OK;
+}
+
+NB200_API int nb200_set_bodies(nb200_ctx* ctx, size_t n, const nb200_real* mass)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(n == 0 || mass == nullptr) { return fail(ctx, NB200_ERR_ARG, "set_bodies: empty body set"); }
+	if(n % static_cast<size_t>(ctx->nshards) != 0)
+	{
+		return fail(ctx, NB200_ERR_ARG, "set_bodies: N = %zu is not a multiple of the shard count %d", n, ctx->nshards);
+	}
+	if(!ctx->live.empty() && ctx->n != 0 && ctx->n != n)
+	{
+		return fail(ctx, NB200_ERR_STATE, "set_bodies: body count changed while buffers are alive");
+	}
+	ctx->n = n;
+	ctx->n_shard = n / static_cast<size_t>(ctx->nshards);
+	ctx->n_pad = (n + NB200_DIRECT_TILE - 1) / NB200_DIRECT_TILE * NB200_DIRECT_TILE;
+	for(auto& l : ctx->lanes)
+	{
+		CU(ctx, cudaSetDevice(l.dev));
+		if(l.mass) { cudaFree(l.mass); l.mass = nullptr; }
+		if(l.src) { cudaFree(l.src); l.src = nullptr; }
+		bh_free(l.bh);
+		l.bh = nullptr;
+		if(cudaMalloc(&l.mass, n * sizeof(real)) != cudaSuccess || cudaMalloc(&l.src, ctx->n_pad * sizeof(body4)) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return fail(ctx, NB200_ERR_ALLOC, "set_bodies: device allocation failed");
+		}
+		// Padding bodies have zero mass: they contribute exactly 0 to every sum.
+		CU(ctx, cudaMemsetAsync(l.src, 0, ctx->n_pad * sizeof(body4), l.stream));
+		CU(ctx, cudaMemcpyAsync(l.mass, mass, n * sizeof(real), cudaMemcpyHostToDevice, l.stream));
+		CU(ctx, cudaStreamSynchronize(l.stream));
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_get_mass(nb200_ctx* ctx, nb200_real* mass)
+{
+	if(ctx == nullptr || mass == nullptr) { return NB200_ERR_ARG; }
+	if(ctx->n == 0) { return fail(ctx, NB200_ERR_STATE, "get_mass: no bodies"); }
+	nb200_lane& l = ctx->lanes[0];
+	CU(ctx, cudaSetDevice(l.dev));
+	CU(ctx, cudaMemcpyAsync(mass, l.mass, ctx->n * sizeof(real), cudaMemcpyDeviceToHost, l.stream));
+	CU(ctx, cudaStreamSynchronize(l.stream));
+	return NB200_OK;
+}
+
+// ---- buffers ---------------------------------------------------------------------
+NB200_API int nb200_alloc(nb200_ctx* ctx, size_t bytes, nb200_buf** out)
+{
+	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
+	*out = nullptr;
+	nb200_buf* b = new nb200_buf();
+	b->owner = ctx;
+	b->bytes = bytes;
+	b->sharded = (ctx->n != 0 && bytes == 6 * ctx->n * sizeof(real));
+	b->lane_elems = b->sharded ? 6 * ctx->n_shard : bytes / sizeof(real);
+	b->lane_bytes = b->sharded ? b->lane_elems * sizeof(real) : bytes;
+	b->dptr.assign(ctx->lanes.size(), nullptr);
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		cudaSetDevice(ctx->lanes[i].dev);
+		if(cudaMalloc(&b->dptr[i], std::max<size_t>(b->lane_bytes, 16)) != cudaSuccess)
+		{
+			cudaGetLastError();
+			for(size_t k = 0; k < i; ++k)
+			{
+				cudaSetDevice(ctx->lanes[k].dev);
+				cudaFree(b->dptr[k]);
+			}
+			delete b;
+			return fail(ctx, NB200_ERR_ALLOC, "alloc: cudaMalloc of %zu bytes failed", bytes);
+		}
+	}
+	ctx->live.insert(b);
+	*out = b;
+	return NB200_OK;
+}
+
+NB200_API int nb200_free(nb200_ctx* ctx, nb200_buf* b)
+{
+	if(b == nullptr) { return NB200_OK; }
+	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "free: not a buffer of this context"); }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		cudaSetDevice(ctx->lanes[i].dev);
+		// cudaFree synchronises the device, so work still using the buffer has finished.
+		cudaFree(b->dptr[i]);
+	}
+	cudaGetLastError();
+	ctx->live.erase(b);
+	b->magic = 0;
+	delete b;
+	return NB200_OK;
+}
+
+NB200_API size_t nb200_size(const nb200_buf* b)
+{
+	return (b != nullptr && b->magic == NB200_BUF_MAGIC) ? b->bytes : 0;
+}
+
+NB200_API int nb200_lane_ptr(nb200_ctx* ctx, nb200_buf* b, int lane, void** dptr, size_t* elems)
+{
+	if(!valid(ctx, b) || lane < 0 || static_cast<size_t>(lane) >= ctx->lanes.size()) { return NB200_ERR_ARG; }
+	if(dptr) { *dptr = b->dptr[static_cast<size_t>(lane)]; }
+	if(elems) { *elems = b->lane_elems; }
+	return NB200_OK;
+}
+
+NB200_API int nb200_write(nb200_ctx* ctx, nb200_buf* dst, const void* host)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, dst)) { return fail(ctx, NB200_ERR_ARG, "write: dst is not a buffer of this context"); }
+	if(host == nullptr) { return fail(ctx, NB200_ERR_ARG, "write: NULL source"); }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		if(dst->sharded)
+		{
+			// 6 rows of N -> 6 rows of n_shard (columns of this shard)
+			const char* src = static_cast<const char*>(host) + static_cast<size_t>(l.shard) * ctx->n_shard * sizeof(real);
+			CU(ctx, cudaMemcpy2DAsync(dst->dptr[i], ctx->n_shard * sizeof(real), src, ctx->n * sizeof(real),
+									  ctx->n_shard * sizeof(real), 6, cudaMemcpyHostToDevice, l.stream));
+		}
+		else if(dst->bytes != 0)
+		{
+			CU(ctx, cudaMemcpyAsync(dst->dptr[i], host, dst->bytes, cudaMemcpyHostToDevice, l.stream));
+		}
+	}
+	return nb200_sync(ctx);	// host memory may be reused as soon as we return
+}
+
+NB200_API int nb200_read(nb200_ctx* ctx, void* host, const nb200_buf* src)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, src)) { return fail(ctx, NB200_ERR_ARG, "read: src is not a buffer of this context"); }
+	if(host == nullptr) { return fail(ctx, NB200_ERR_ARG, "read: NULL destination"); }
+	if(!src->sharded)
+	{
+		nb200_lane& l = ctx->lanes[0];
+		CU(ctx, cudaSetDevice(l.dev));
+		if(src->bytes != 0)
+		{
+			CU(ctx, cudaMemcpyAsync(host, src->dptr[0], src->bytes, cudaMemcpyDeviceToHost, l.stream));
+		}
+		CU(ctx, cudaStreamSynchronize(l.stream));
+		return NB200_OK;
+	}
+	if(ctx->nranks > 1)
+	{
+		// All ranks call read at the same point: gather the shards, then un-interleave on the host.
+		nb200_lane&	l = ctx->lanes[0];
+		real*		all = nullptr;
+		CU(ctx, cudaSetDevice(l.dev));
+		if(cudaMalloc(&all, src->bytes) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return fail(ctx, NB200_ERR_ALLOC, "read: gather scratch allocation failed");
+		}
+		ncclResult_t r = ctx->nccl->AllGather(src->dptr[0], all, src->lane_elems, NB200_NCCL_REAL,
+											  static_cast<ncclComm_t>(ctx->comm), l.stream);
+		if(r != ncclSuccess)
+		{
+			cudaFree(all);
+			return fail(ctx, NB200_ERR_NCCL, "read: ncclAllGather: %s", ctx->nccl->GetErrorString(r));
+		}
+		cudaError_t ce = cudaSuccess;
+		for(int g = 0; g < ctx->nshards && ce == cudaSuccess; ++g)
+		{
+			char* dst = static_cast<char*>(host) + static_cast<size_t>(g) * ctx->n_shard * sizeof(real);
+			ce = cudaMemcpy2DAsync(dst, ctx->n * sizeof(real), all + static_cast<size_t>(g) * src->lane_elems,
+								   ctx->n_shard * sizeof(real), ctx->n_shard * sizeof(real), 6, cudaMemcpyDeviceToHost, l.stream);
+		}
+		if(ce == cudaSuccess) { ce = cudaStreamSynchronize(l.stream); }
+		cudaFree(all);
+		if(ce != cudaSuccess) { return fail(ctx, NB200_ERR_CUDA, "read: %s", cudaGetErrorString(ce)); }
+		return NB200_OK;
+	}
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		char* dst = static_cast<char*>(host) + static_cast<size_t>(l.shard) * ctx->n_shard * sizeof(real);
+		CU(ctx, cudaMemcpy2DAsync(dst, ctx->n * sizeof(real), src->dptr[i], ctx->n_shard * sizeof(real),
+								  ctx->n_shard * sizeof(real), 6, cudaMemcpyDeviceToHost, l.stream));
+	}
+	return nb200_sync(ctx);
+}
+
+NB200_API int nb200_copy(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "copy: a is not a buffer of this context"); }
+	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "copy: b is not a buffer of this context"); }
+	if(a->bytes != b->bytes) { return fail(ctx, NB200_ERR_ARG, "copy: size does not match"); }
+	if(a == b || a->lane_bytes == 0) { return NB200_OK; }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		CU(ctx, cudaMemcpyAsync(a->dptr[i], b->dptr[i], a->lane_bytes, cudaMemcpyDeviceToDevice, l.stream));
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_fill(nb200_ctx* ctx, nb200_buf* a, nb200_real value)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fill: a is not a buffer of this context"); }
+	if(a->lane_elems == 0) { return NB200_OK; }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		ew_fill<<<ew_grid(l, a->lane_elems), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), value, a->lane_elems);
+		LAUNCHED(ctx);
+	}
+	return NB200_OK;
+}
+
+// ---- direct all-pairs --------------------------------------------------------------
+NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f)
+{
+	int rc = check_state_pair(ctx, y, f, "fcompute_direct");
+	if(rc != NB200_OK) { return rc; }
+	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_direct: y and f must differ"); }
+	rc = pack_and_gather(ctx, y);
+	if(rc != NB200_OK) { return rc; }
+
+	const int	n_tiles = static_cast<int>(ctx->n_pad / NB200_DIRECT_TILE);
+	const int	sms = ctx->lanes[0].sm_count;
+	// Targets per thread: as many as still leave >= 2 CTAs per SM worth of (target block, tile) items.
+	int ipt = 1;
+	if(ctx->opt_direct_ipt == 1 || ctx->opt_direct_ipt == 2 || ctx->opt_direct_ipt == 4)
+	{
+		ipt = static_cast<int>(ctx->opt_direct_ipt);
+	}
+	else
+	{
+		for(int cand = 4; cand >= 1; cand >>= 1)
+		{
+			size_t blocks = (ctx->n_shard + NB200_DIRECT_THREADS * cand - 1) / (NB200_DIRECT_THREADS * cand);
+			if(blocks * static_cast<size_t>(n_tiles) >= static_cast<size_t>(2 * sms) || cand == 1)
+			{
+				ipt = cand;
+				break;
+			}
+		}
+	}
+	const size_t	i_blocks = (ctx->n_shard + NB200_DIRECT_THREADS * ipt - 1) / (NB200_DIRECT_THREADS * ipt);
+	// Source segments: enough equal work items (~48 per SM) that the last wave costs <~ 2 %.
+	size_t want = static_cast<size_t>(sms) * 48;
+	size_t seg = (want + i_blocks - 1) / i_blocks;
+	if(ctx->opt_direct_segments > 0) { seg = static_cast<size_t>(ctx->opt_direct_segments); }
+	seg = std::max<size_t>(1, std::min<size_t>(seg, std::min<size_t>(static_cast<size_t>(n_tiles), 64)));
+	const int	tiles_per_seg = static_cast<int>((static_cast<size_t>(n_tiles) + seg - 1) / seg);
+	const int	segments = (n_tiles + tiles_per_seg - 1) / tiles_per_seg;
+
+	for(size_t li = 0; li < ctx->lanes.size(); ++li)
+	{
+		nb200_lane& l = ctx->lanes[li];
+		CU(ctx, cudaSetDevice(l.dev));
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[2], l.stream)); }
+		real* out = lane_ptr(f, li);
+		if(segments > 1)
+		{
+			size_t need = static_cast<size_t>(segments) * 3 * ctx->n_shard;
+			if(l.partial_elems < need)
+			{
+				if(l.partial) { cudaFree(l.partial); l.partial = nullptr; l.partial_elems = 0; }
+				if(cudaMalloc(&l.partial, need * sizeof(real)) != cudaSuccess)
+				{
+					cudaGetLastError();
+					return fail(ctx, NB200_ERR_ALLOC, "fcompute_direct: partial-sum scratch allocation failed");
+				}
+				l.partial_elems = need;
+			}
+			out = l.partial;
+		}
+		dim3 grid(static_cast<unsigned>(i_blocks), static_cast<unsigned>(segments));
+		const int write_f = segments == 1 ? 1 : 0;
+		switch(ipt)
+		{
+		case 4: launch_pairs<4>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;
+		case 2: launch_pairs<2>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;
+		default: launch_pairs<1>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;
+		}
+		LAUNCHED(ctx);
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[3], l.stream)); }
+		if(segments > 1)
+		{
+			unsigned rgrid = static_cast<unsigned>((3 * ctx->n_shard + 255) / 256);
+			direct_reduce<<<rgrid, 256, 0, l.stream>>>(l.partial, lane_ptr(y, li), lane_ptr(f, li), ctx->n_shard, segments);
+			LAUNCHED(ctx);
+		}
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }
+	}
+	return NB200_OK;
+}
+
+// ---- Barnes-Hut ------------------------------------------------------------------------
+NB200_API int nb200_bh_configure(nb200_ctx* ctx, nb200_real ratio, int layout, size_t tree_build_rate)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(layout != NB200_TREE_HEAP && layout != NB200_TREE_HEAP_STACKLESS)
+	{
+		return fail(ctx, NB200_ERR_ARG, "bh_configure: tree_layout must be heap or heap_stackless");
+	}
+	ctx->bh_ratio = ratio;
+	ctx->bh_layout = layout;
+	ctx->bh_build_rate = tree_build_rate;
+	return NB200_OK;
+}
+
+NB200_API int nb200_fcompute_bh(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, size_t step)
+{
+	int rc = check_state_pair(ctx, y, f, "fcompute_bh");
+	if(rc != NB200_OK) { return rc; }
+	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_bh: y and f must differ"); }
+	if((ctx->n & (ctx->n - 1)) != 0)
+	{
+		return fail(ctx, NB200_ERR_UNSUPPORTED, "fcompute_bh: N = %zu is not a power of two (kd-heap leaves are [N, 2N))", ctx->n);
+	}
+	rc = pack_and_gather(ctx, y);
+	if(rc != NB200_OK) { return rc; }
+	for(size_t li = 0; li < ctx->lanes.size(); ++li)
+	{
+		nb200_lane& l = ctx->lanes[li];
+		CU(ctx, cudaSetDevice(l.dev));
+		std::string err;
+		int launches = 0;
+		rc = bh_fcompute(ctx, l, lane_ptr(y, li), lane_ptr(f, li), step, launches, err);
+		ctx->launches += static_cast<unsigned long long>(launches);
+		if(rc != NB200_OK) { return fail(ctx, rc, "fcompute_bh: %s", err.c_str()); }
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_bh_export_tree(nb200_ctx* ctx, int lane, nb200_real* xyzr, nb200_real* mass, int* body_n)
+{
+	if(ctx == nullptr || lane < 0 || static_cast<size_t>(lane) >= ctx->lanes.size()) { return NB200_ERR_ARG; }
+	nb200_lane& l = ctx->lanes[static_cast<size_t>(lane)];
+	if(l.bh == nullptr) { return fail(ctx, NB200_ERR_STATE, "bh_export_tree: no tree has been built"); }
+	CU(ctx, cudaSetDevice(l.dev));
+	std::string err;
+	int rc = bh_export(ctx, l, xyzr, mass, body_n, err);
+	if(rc != NB200_OK) { return fail(ctx, rc, "bh_export_tree: %s", err.c_str()); }
+	return NB200_OK;
+}
+
+NB200_API int nb200_bh_walk_stats(nb200_ctx* ctx, int enable, unsigned long long* visits, unsigned long long* interactions)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	unsigned long long v = 0, k = 0;
+	if(ctx->bh_stats)
+	{
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			CU(ctx, cudaMemcpyAsync(l.h_scalar + 2, l.d_scalar + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+			CU(ctx, cudaStreamSynchronize(l.stream));
+			v += l.h_scalar[2];
+			k += l.h_scalar[3];
+		}
+	}
+	if(visits) { *visits = v; }
+	if(interactions) { *interactions = k; }
+	ctx->bh_stats = enable != 0;
+	return NB200_OK;
+}
+
+// ---- state-vector ops ---------------------------------------------------------------------
+NB200_API int nb200_fmadd_inplace(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, nb200_real c)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: a is not a buffer of this context"); }
+	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: b is not a buffer of this context"); }
+	if(a->bytes != b->bytes) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: size does not match"); }
+	if(a->lane_elems == 0) { return NB200_OK; }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		ew_fmadd_inplace<<<ew_grid(l, a->lane_elems), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), lane_ptr(b, i), c, a->lane_elems);
+		LAUNCHED(ctx);
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_fmadd(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, const nb200_buf* c, nb200_real d)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmadd: a is not a buffer of this context"); }
+	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd: b is not a buffer of this context"); }
+	if(!valid(ctx, c)) { return fail(ctx, NB200_ERR_ARG, "fmadd: c is not a buffer of this context"); }
+	if(a->bytes != b->bytes || a->bytes != c->bytes) { return fail(ctx, NB200_ERR_ARG, "fmadd: size does not match"); }
+	if(a->lane_elems == 0) { return NB200_OK; }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		ew_fmadd<<<ew_grid(l, a->lane_elems), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), lane_ptr(b, i), lane_ptr(c, i), d, a->lane_elems);
+		LAUNCHED(ctx);
+	}
+	return NB200_OK;
+}
+
+namespace {
+// Shared body of fmaddn / fmaddn_inplace / fmaddn_corr.
+//   base: starting value (NULL = zeros); for the in-place forms base == a.
+//   corr: non-NULL selects the Kahan kernel.
+int fused_terms(nb200_ctx* ctx, const char* who, nb200_buf* a, const nb200_buf* base, nb200_buf* corr,
+				const nb200_buf* const* terms, const nb200_real* coeff, size_t n, bool keep_a_if_no_terms)
+{
+	// Collect non-zero terms first: zero coefficients are skipped before their buffers are even looked at
+	// (nbody/nbody_engine.cpp:58-63,95-99).
+	std::vector<size_t> used;
+	for(size_t k = 0; k < n; ++k)
+	{
+		if(coeff[k] == static_cast<real>(0)) { continue; }
+		if(terms == nullptr || !valid(ctx, terms[k]))
+		{
+			return fail(ctx, NB200_ERR_ARG, "%s: term %zu is not a buffer of this context", who, k);
+		}
+		if(terms[k]->bytes != a->bytes) { return fail(ctx, NB200_ERR_ARG, "%s: term %zu size does not match", who, k); }
+		used.push_back(k);
+	}
+	if(used.empty())
+	{
+		if(keep_a_if_no_terms) { return NB200_OK; }	// a is left untouched, as in the reference
+		return nb200_fill(ctx, a, 0);				// fmaddn with b == NULL: a = 0
+	}
+	if(a->lane_elems == 0) { return NB200_OK; }
+	for(size_t first = 0; first < used.size(); first += NB200_MAX_TERMS)
+	{
+		size_t cnt = std::min<size_t>(NB200_MAX_TERMS, used.size() - first);
+		for(size_t i = 0; i < ctx->lanes.size(); ++i)
+		{
+			nb200_lane& l = ctx->lanes[i];
+			CU(ctx, cudaSetDevice(l.dev));
+			nb200_terms t;
+			t.n = static_cast<int>(cnt);
+			for(size_t k = 0; k < cnt; ++k)
+			{
+				t.p[k] = lane_ptr(terms[used[first + k]], i);
+				t.c[k] = coeff[used[first + k]];
+			}
+			unsigned grid = ew_grid(l, a->lane_elems);
+			if(corr != nullptr)
+			{
+				ew_fmaddn_corr<<<grid, NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), lane_ptr(corr, i), t, a->lane_elems);
+			}
+			else
+			{
+				const real* b0 = (first == 0) ? (base != nullptr ? lane_ptr(base, i) : nullptr) : lane_ptr(a, i);
+				ew_fmaddn<<<grid, NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), b0, t, a->lane_elems);
+			}
+			LAUNCHED(ctx);
+		}
+	}
+	return NB200_OK;
+}
+}  // namespace
+
+NB200_API int nb200_fmaddn_inplace(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* const* b, const nb200_real* c, size_t n)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(c == nullptr) { return fail(ctx, NB200_ERR_ARG, "fmaddn_inplace: c == NULL"); }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_inplace: a is not a buffer of this context"); }
+	return fused_terms(ctx, "fmaddn_inplace", a, a, nullptr, b, c, n, true);
+}
+
+NB200_API int nb200_fmaddn(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, const nb200_buf* const* c, const nb200_real* d, size_t n)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(d == nullptr) { return fail(ctx, NB200_ERR_ARG, "fmaddn: d == NULL"); }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaddn: a is not a buffer of this context"); }
+	if(b != nullptr)
+	{
+		if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmaddn: b is not a buffer of this context"); }
+		if(a->bytes != b->bytes) { return fail(ctx, NB200_ERR_ARG, "fmaddn: size does not match"); }
+	}
+	// Reference quirk kept: with b != NULL and no non-zero term, a is NOT assigned (nbody_engine.cpp:87-112).
+	return fused_terms(ctx, "fmaddn", a, b, nullptr, c, d, n, b != nullptr);
+}
+
+NB200_API int nb200_fmaddn_corr(nb200_ctx* ctx, nb200_buf* a, nb200_buf* corr, const nb200_buf* const* b, const nb200_real* c, size_t n)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: a is not a buffer of this context"); }
+	if(!valid(ctx, corr)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: corr is not a buffer of this context"); }
+	if(c == nullptr) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: c == NULL"); }
+	if(a->bytes != corr->bytes) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: size does not match"); }
+	if(a == corr) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: a and corr must differ"); }
+	// The reference validates every b[k], zero coefficient or not (nbody_engine_cuda.cpp:431-439).
+	for(size_t k = 0; k < n; ++k)
+	{
+		if(b == nullptr || !valid(ctx, b[k])) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: b[%zu] is not a buffer of this context", k); }
+	}
+	return fused_terms(ctx, "fmaddn_corr", a, a, corr, b, c, n, true);
+}
+
+NB200_API int nb200_fmaxabs(nb200_ctx* ctx, const nb200_buf* a, nb200_real* result)
+{
+	if(ctx == nullptr || result == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaxabs: a is not a buffer of this context"); }
+	if(a->lane_elems == 0)
+	{
+		*result = 0;
+		return NB200_OK;
+	}
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		CU(ctx, cudaMemsetAsync(l.d_scalar, 0, sizeof(unsigned long long), l.stream));
+		ew_maxabs<<<ew_grid(l, a->lane_elems), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), a->lane_elems, l.d_scalar);
+		LAUNCHED(ctx);
+		if(ctx->nranks > 1)
+		{
+			// Bit patterns of non-negative reals order like unsigned integers: max over ranks is exact.
+			NC(ctx, ctx->nccl->AllReduce(l.d_scalar, l.d_scalar, 1, ncclUint64, ncclMax, static_cast<ncclComm_t>(ctx->comm), l.stream));
+		}
+		CU(ctx, cudaMemcpyAsync(l.h_scalar, l.d_scalar, sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+	}
+	unsigned long long best = 0;
+	for(auto& l : ctx->lanes)
+	{
+		CU(ctx, cudaSetDevice(l.dev));
+		CU(ctx, cudaStreamSynchronize(l.stream));
+		best = std::max(best, l.h_scalar[0]);
+	}
+#if NB200_PRECISION == 2
+	double out;
+	memcpy(&out, &best, sizeof(out));
+#else
+	unsigned int b32 = static_cast<unsigned int>(best);
+	float out;
+	memcpy(&out, &b32, sizeof(out));
+#endif
+	*result = out;
+	return NB200_OK;
+}
+
+NB200_API int nb200_clamp(nb200_ctx* ctx, nb200_buf* y, nb200_real b)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "clamp: y is not a buffer of this context"); }
+	if(!y->sharded) { return fail(ctx, NB200_ERR_ARG, "clamp: y must be a state vector of 6*N elements"); }
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		size_t count3 = 3 * ctx->n_shard;	// the three position rows are contiguous in a shard
+		ew_clamp<<<static_cast<unsigned>((count3 + NB200_EW_THREADS - 1) / NB200_EW_THREADS), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(y, i), b, count3);
+		LAUNCHED(ctx);
+	}
+	return NB200_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------
+NB200_API unsigned long long nb200_launch_count(const nb200_ctx* ctx)
+{
+	return ctx != nullptr ? ctx->launches : 0;
+}
+
+NB200_API int nb200_last_fcompute_ms(nb200_ctx* ctx, float out[4])
+{
+	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
+	nb200_lane& l = ctx->lanes[0];
+	CU(ctx, cudaSetDevice(l.dev));
+	CU(ctx, cudaStreamSynchronize(l.stream));
+	for(int i = 0; i < 4; ++i)
+	{
+		out[i] = 0;
+		if(cudaEventElapsedTime(&out[i], l.ev_t[i], l.ev_t[i + 1]) != cudaSuccess)
+		{
+			cudaGetLastError();
+			out[i] = 0;
+		}
+	}
+	return NB200_OK;
+}
+
+NB200_API int nb200_mark(nb200_ctx* ctx, int slot)
+{
+	if(ctx == nullptr || slot < 0 || slot >= 8) { return NB200_ERR_ARG; }
+	nb200_lane& l = ctx->lanes[0];
+	CU(ctx, cudaSetDevice(l.dev));
+	CU(ctx, cudaEventRecord(l.ev_mark[slot], l.stream));
+	return NB200_OK;
+}
+
+NB200_API int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms)
+{
+	if(ctx == nullptr || ms == nullptr || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) { return NB200_ERR_ARG; }
+	nb200_lane& l = ctx->lanes[0];
+	CU(ctx, cudaSetDevice(l.dev));
+	CU(ctx, cudaEventSynchronize(l.ev_mark[slot_b]));
+	CU(ctx, cudaEventElapsedTime(ms, l.ev_mark[slot_a], l.ev_mark[slot_b]));
+	return NB200_OK;
+}
+
+NB200_API int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s)
+{
+	if(ctx == nullptr || fma_lane_per_s == nullptr) { return NB200_ERR_ARG; }
+	nb200_lane& l = ctx->lanes[0];
+	CU(ctx, cudaSetDevice(l.dev));
+	cudaEvent_t e0, e1;
+	CU(ctx, cudaEventCreate(&e0));
+	CU(ctx, cudaEventCreate(&e1));
+	const int		blocks = l.sm_count * 8;
+	int				iters = 256;
+	float			elapsed = 0;
+	double			best = 0;
+	// Grow the launch until one run lasts >= ms/4, then keep the best of 4 such runs.
+	for(int run = 0, timed = 0; run < 40 && timed < 4; ++run)
+	{
+		cudaEventRecord(e0, l.stream);
+		probe_fma<<<blocks, 256, 0, l.stream>>>(reinterpret_cast<real*>(l.d_scalar + 4), iters, static_cast<real>(1.0));
+		++ctx->launches;
+		cudaEventRecord(e1, l.stream);
+		CU(ctx, cudaEventSynchronize(e1));
+		CU(ctx, cudaEventElapsedTime(&elapsed, e0, e1));
+		if(elapsed * 4 >= ms || iters >= (1 << 24))
+		{
+			best = std::max(best, static_cast<double>(blocks) * 256.0 * iters * 64.0 / (elapsed * 1e-3));
+			++timed;
+		}
+		else
+		{
+			iters *= 2;
+		}
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	*fma_lane_per_s = best;
+	return NB200_OK;
+}
+
+NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value)
+{
+	if(ctx == nullptr || name == nullptr) { return NB200_ERR_ARG; }
+	if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
+	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
+	else if(strcmp(name, "walk_block") == 0) { ctx->opt_walk_block = value; }
+	else if(strcmp(name, "timing") == 0) { ctx->opt_timing = value; }
+	else { return fail(ctx, NB200_ERR_ARG, "set_option: unknown option %s", name); }
+	return NB200_OK;
+}

@@ -1,0 +1,101 @@
+// nb200 -- shared types for the sm_100a kernels and the C ABI (include/nb200.h).
+#ifndef NB200_COMMON_CUH
+#define NB200_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <unordered_set>
+
+#include "../../include/nb200.h"
+
+typedef nb200_real real;
+
+// Packed source body: position + mass, the unit the all-pairs kernel streams
+// through shared memory (one 32-byte / 16-byte vector per body).
+#if NB200_PRECISION == 1
+struct alignas(16) body4 { float x, y, z, m; };
+#define NB200_MIN_DISTANCE 1e-8f
+#else
+struct alignas(32) body4 { double x, y, z, m; };
+#define NB200_MIN_DISTANCE 1e-8
+#endif
+
+// nbody::MinDistance (nbody/nbtype.h:78): r^2 is clamped to this value.
+
+#define NB200_MAX_TERMS 48  // fused fmaddn terms per launch (rkfeagin14 needs 35)
+
+struct nb200_terms
+{
+	const real*	p[NB200_MAX_TERMS];
+	real		c[NB200_MAX_TERMS];
+	int			n;
+};
+
+#define NB200_BUF_MAGIC 0x6e62323030627566ULL
+
+struct bh_state;
+
+struct nb200_lane
+{
+	int				dev = 0;
+	int				shard = 0;          // global shard index of this lane
+	int				sm_count = 148;
+	cudaStream_t	stream = nullptr;
+	cudaEvent_t		ev_packed = nullptr;   // "my packed shard is ready" (local gather)
+	cudaEvent_t		ev_gathered = nullptr; // "I finished reading peers' shards"
+	cudaEvent_t		ev_t[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase timing of the last fcompute
+	cudaEvent_t		ev_mark[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // nb200_mark
+	real*			mass = nullptr;     // N masses (full copy)
+	body4*			src = nullptr;      // packed sources for all N bodies (+ zero-mass padding)
+	real*			partial = nullptr;  // [S][3][n_shard] partial accelerations (direct, S>1)
+	size_t			partial_elems = 0;
+	unsigned long long*	d_scalar = nullptr;	// device scratch: maxabs bits, walk counters (4 x u64)
+	unsigned long long*	h_scalar = nullptr;	// pinned mirror
+	bh_state*		bh = nullptr;
+};
+
+struct nccl_api;
+
+struct nb200_ctx
+{
+	std::vector<nb200_lane>	lanes;
+	int			rank = 0;
+	int			nranks = 1;
+	int			nshards = 1;
+	int			first_shard = 0;
+	size_t		n = 0;          // bodies
+	size_t		n_shard = 0;    // bodies per shard
+	size_t		n_pad = 0;      // packed source count incl. padding
+	nccl_api*	nccl = nullptr;
+	void*		comm = nullptr; // ncclComm_t
+	std::unordered_set<const nb200_buf*>	live;
+	unsigned long long	launches = 0;
+	std::string	err;
+	// Barnes-Hut configuration
+	real		bh_ratio = 10;
+	int			bh_layout = NB200_TREE_HEAP_STACKLESS;
+	size_t		bh_build_rate = 0;
+	bool		bh_stats = false;
+	// tunables (0 = automatic)
+	long long	opt_direct_ipt = 0;
+	long long	opt_direct_segments = 0;
+	long long	opt_walk_block = 0;
+	long long	opt_timing = 1;
+};
+
+struct nb200_buf
+{
+	unsigned long long	magic = NB200_BUF_MAGIC;
+	nb200_ctx*			owner = nullptr;
+	size_t				bytes = 0;        // logical size
+	bool				sharded = false;  // state vector: 6 rows x n_shard per lane
+	size_t				lane_elems = 0;   // real elements held by each lane
+	size_t				lane_bytes = 0;
+	std::vector<void*>	dptr;             // one allocation per lane
+};
+
+#endif // NB200_COMMON_CUH

@@ -1,0 +1,254 @@
+// nb200 -- direct all-pairs gravity for sm_100a.
+//
+// Replaces the reference's kfcompute + kfcompute_xyz
+// (nbody/nbody_engine_cuda_impl.cu:10-124). Same mathematics as the CPU
+// engines (nbody/nbody_data.cpp:35-44, nbody/nbody_engine_block.cpp:93-112):
+//
+//     a_i = sum_j m_j (r_j - r_i) / max(|r_j - r_i|^2, MinDistance)^(3/2)
+//
+// including j == i, which contributes exactly 0 (dr = 0).
+//
+// Shape of the kernel
+//   * sources are streamed as packed body4 {x,y,z,m} tiles; one elected thread
+//     issues a TMA bulk copy (cp.async.bulk -> UBLKCP) per tile into a 3-stage
+//     shared-memory ring, completion is signalled through an mbarrier;
+//   * every thread owns IPT targets in registers, so one broadcast LDS.128
+//     pair feeds IPT pair interactions (i-blocking);
+//   * r^-3 comes from MUFU.RSQ64H + one cubically convergent correction
+//     (17 FP64-pipe instructions per pair, no sqrt, no divide, no slow path);
+//   * the grid is (target blocks) x (source segments): splitting the source
+//     range makes the number of equal-sized work items >> 148 SMs for every N
+//     (N = 16 ... 4M, 1 ... 8 shards), partial sums are combined in a fixed
+//     order by direct_reduce so results are bit-reproducible run to run.
+#ifndef NB200_DIRECT_CUH
+#define NB200_DIRECT_CUH
+
+#include "nb200_common.cuh"
+
+#define NB200_DIRECT_THREADS 128
+#define NB200_DIRECT_TILE 128     // bodies per shared-memory tile
+#define NB200_DIRECT_STAGES 3
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX ISA 8.x, sm_90+) ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile(
+		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+		"l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+		: "memory");
+}
+
+// ---- one pair interaction --------------------------------------------------
+#if NB200_PRECISION == 2
+__device__ __forceinline__ void pair_interaction(double xi, double yi, double zi, const body4& s,
+												 double& ax, double& ay, double& az)
+{
+	double	dx = s.x - xi;
+	double	dy = s.y - yi;
+	double	dz = s.z - zi;
+	double	r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+	// r2 = max(r2, MinDistance) on the integer pipe: r2 >= +0, so the IEEE bit
+	// patterns order like signed integers (keeps the FP64 pipe for arithmetic).
+	long long		bits = __double_as_longlong(r2);
+	const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8
+	bits = bits < min_bits ? min_bits : bits;
+	r2 = __longlong_as_double(bits);
+	// y0 ~ r2^-1/2 to ~2^-20 (MUFU.RSQ64H); e = 1 - r2*y0^2;
+	// r2^-1/2 = y0 (1-e)^-1/2 = y0 (1 + e/2 + 3e^2/8) + O(e^3) ~ 2^-60.
+	double	y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+	double	h = r2 * y0;
+	double	e = fma(-h, y0, 1.0);
+	double	p = fma(e, 0.375, 0.5);
+	double	q = y0 * e;
+	double	y = fma(q, p, y0);
+	double	c = (y * y) * (s.m * y);
+	ax = fma(dx, c, ax);
+	ay = fma(dy, c, ay);
+	az = fma(dz, c, az);
+}
+#else
+__device__ __forceinline__ void pair_interaction(float xi, float yi, float zi, const body4& s,
+												 float& ax, float& ay, float& az)
+{
+	float	dx = s.x - xi;
+	float	dy = s.y - yi;
+	float	dz = s.z - zi;
+	float	r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+	r2 = fmaxf(r2, NB200_MIN_DISTANCE);
+	float	y = rsqrtf(r2);		// MUFU.RSQ, <= 2 ulp
+	float	c = (y * y) * (s.m * y);
+	ax = fmaf(dx, c, ax);
+	ay = fmaf(dy, c, ay);
+	az = fmaf(dz, c, az);
+}
+#endif
+
+// src_all[shard_first + i] = {x, y, z, m} for the local shard's bodies.
+__global__ void __launch_bounds__(256) direct_pack(const real* __restrict__ y, const real* __restrict__ mass,
+												   body4* __restrict__ src, size_t n_shard, size_t shard_first)
+{
+	size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(i >= n_shard)
+	{
+		return;
+	}
+	body4 b;
+	b.x = y[i];
+	b.y = y[n_shard + i];
+	b.z = y[2 * n_shard + i];
+	b.m = mass[shard_first + i];
+	src[shard_first + i] = b;
+}
+
+// grid = (ceil(n_shard / (THREADS*IPT)), segments)
+// out: segments == 1 -> f (acc rows at 3n,4n,5n; velocity rows copied to 0..3n)
+//      segments  > 1 -> partial[seg][3][n_shard]
+template<int IPT>
+__global__ void __launch_bounds__(NB200_DIRECT_THREADS)
+direct_pairs(const body4* __restrict__ src, const real* __restrict__ y, real* __restrict__ out,
+			 size_t n_shard, size_t shard_first, int n_tiles, int tiles_per_seg, int write_f)
+{
+	__shared__ body4					tile[NB200_DIRECT_STAGES][NB200_DIRECT_TILE];
+	__shared__ alignas(8) uint64_t		full[NB200_DIRECT_STAGES];
+
+	const int	tid = threadIdx.x;
+	const int	t_begin = blockIdx.y * tiles_per_seg;
+	const int	t_end = min(n_tiles, t_begin + tiles_per_seg);
+	const int	nt = t_end - t_begin;
+	const uint32_t tile_bytes = NB200_DIRECT_TILE * sizeof(body4);
+
+	if(tid == 0)
+	{
+		for(int s = 0; s < NB200_DIRECT_STAGES; ++s)
+		{
+			mbar_init(&full[s], 1);
+		}
+		mbar_fence_init();
+	}
+	__syncthreads();
+	if(tid == 0)
+	{
+		for(int s = 0; s < NB200_DIRECT_STAGES - 1 && s < nt; ++s)
+		{
+			mbar_expect_tx(&full[s], tile_bytes);
+			tma_bulk_g2s(&tile[s][0], src + static_cast<size_t>(t_begin + s) * NB200_DIRECT_TILE, tile_bytes, &full[s]);
+		}
+	}
+
+	real	xi[IPT], yi[IPT], zi[IPT], ax[IPT], ay[IPT], az[IPT];
+	const size_t	i0 = static_cast<size_t>(blockIdx.x) * (NB200_DIRECT_THREADS * IPT) + tid;
+#pragma unroll
+	for(int k = 0; k < IPT; ++k)
+	{
+		size_t	i = i0 + static_cast<size_t>(k) * NB200_DIRECT_THREADS;
+		size_t	ic = i < n_shard ? i : n_shard - 1;	// out-of-range lanes compute a duplicate, never store
+		body4	b = src[shard_first + ic];
+		xi[k] = b.x;
+		yi[k] = b.y;
+		zi[k] = b.z;
+		ax[k] = ay[k] = az[k] = 0;
+	}
+
+	for(int t = 0; t < nt; ++t)
+	{
+		const int	stage = t % NB200_DIRECT_STAGES;
+		// Refill the stage consumed in iteration t-1 (all threads passed its closing barrier).
+		if(tid == 0)
+		{
+			int tn = t + NB200_DIRECT_STAGES - 1;
+			if(tn < nt)
+			{
+				int sn = tn % NB200_DIRECT_STAGES;
+				mbar_expect_tx(&full[sn], tile_bytes);
+				tma_bulk_g2s(&tile[sn][0], src + static_cast<size_t>(t_begin + tn) * NB200_DIRECT_TILE, tile_bytes, &full[sn]);
+			}
+		}
+		mbar_wait(&full[stage], (t / NB200_DIRECT_STAGES) & 1);
+		const body4*	tb = &tile[stage][0];
+#pragma unroll 4
+		for(int j = 0; j < NB200_DIRECT_TILE; ++j)
+		{
+			const body4	s = tb[j];	// warp-uniform address: broadcast LDS.128 (x2 for FP64)
+#pragma unroll
+			for(int k = 0; k < IPT; ++k)
+			{
+				pair_interaction(xi[k], yi[k], zi[k], s, ax[k], ay[k], az[k]);
+			}
+		}
+		__syncthreads();
+	}
+
+#pragma unroll
+	for(int k = 0; k < IPT; ++k)
+	{
+		size_t	i = i0 + static_cast<size_t>(k) * NB200_DIRECT_THREADS;
+		if(i < n_shard)
+		{
+			if(write_f)
+			{
+				out[i] = y[3 * n_shard + i];
+				out[n_shard + i] = y[4 * n_shard + i];
+				out[2 * n_shard + i] = y[5 * n_shard + i];
+				out[3 * n_shard + i] = ax[k];
+				out[4 * n_shard + i] = ay[k];
+				out[5 * n_shard + i] = az[k];
+			}
+			else
+			{
+				real*	p = out + static_cast<size_t>(blockIdx.y) * 3 * n_shard;
+				p[i] = ax[k];
+				p[n_shard + i] = ay[k];
+				p[2 * n_shard + i] = az[k];
+			}
+		}
+	}
+}
+
+// f[0..3n) = y[3n..6n);  f[3n + r*n + i] = sum_s partial[s][r][i]  (s ascending: fixed order)
+__global__ void __launch_bounds__(256) direct_reduce(const real* __restrict__ partial, const real* __restrict__ y,
+													 real* __restrict__ f, size_t n_shard, int segments)
+{
+	size_t	e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;	// element of the 3 x n_shard block
+	if(e >= 3 * n_shard)
+	{
+		return;
+	}
+	real	acc = 0;
+	for(int s = 0; s < segments; ++s)
+	{
+		acc += partial[static_cast<size_t>(s) * 3 * n_shard + e];
+	}
+	f[e] = y[3 * n_shard + e];
+	f[3 * n_shard + e] = acc;
+}
+
+#endif // NB200_DIRECT_CUH

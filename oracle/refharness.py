@@ -30,11 +30,12 @@ def _sig(lib, name, restype, *argtypes):
 
 
 def load(precision="f64"):
-    """Load (once) and type the nbref_* entry points. RTLD_GLOBAL so that the
-    nb200 adapter library resolves the nbody_engine base-class symbols."""
+    """Load (once) and type the nbref_* entry points. RTLD_LOCAL: the f64 and f32
+    builds define the same C++ symbols with different layouts and must not see
+    each other; the nb200 adapter library links its libnbref_* explicitly."""
     if precision in _LIBS:
         return _LIBS[precision]
-    lib = C.CDLL(lib_path(precision), mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(lib_path(precision), mode=C.RTLD_LOCAL)
     vp, sz, dbl, cs, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int
     _sig(lib, "nbref_coord_size", i32)
     _sig(lib, "nbref_max_threads", i32)

@@ -1,0 +1,133 @@
+"""Parity of the CUDA direct all-pairs fcompute (through the C ABI) with the
+reference's engines / the CPU oracle. Gate: per-body relative error of the
+acceleration <= 1e-12 in FP64 (BASELINE.json north_star), ~1e-5 in FP32."""
+import numpy as np
+import pytest
+
+from conftest import load_golden_npz, golden_path, rel_err_per_body
+from util import universe
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 2e-5
+
+
+def run_direct(y, m, precision="f64", devices="0", options=()):
+    from nbody_b200 import Engine
+    with Engine(precision=precision, devices=devices) as e:
+        for k, v in options:
+            e.set_option(k, v)
+        assert e.init(y, m)
+        f = e.create_buffer(e.get_y().size())
+        e.fill_buffer(f, -1e10)
+        e.fcompute(0.0, e.get_y(), f)
+        out = e.read_buffer(f)
+        assert e.get_compute_count() == 1 and e.launch_count() >= 2
+        e.free_buffer(f)
+    return out
+
+
+@pytest.mark.parametrize("tag,n", [("g1_n128", 128), ("g1_n256", 256), ("g1_n2048", 2048)])
+def test_direct_vs_reference_engines_fp64(tag, n):
+    g = load_golden_npz(tag)
+    f = run_direct(g["y"], g["mass"])
+    assert np.array_equal(f[:3 * n], g["y"][3 * n:])          # dr/dt = v, bit-exact
+    assert rel_err_per_body(f, g["f_openmp"], n) <= TOL64
+    assert rel_err_per_body(f, g["f_block"], n) <= TOL64
+    # the reference's own cross-engine gate: |df| <= 1e-13 absolute vs nbody_engine_simple
+    # (test_nbody_engine.cpp:472-558, default m_eps) holds for the accelerations of this fixture
+    assert np.abs(f - g["f_simple"]).max() <= 1e-13 * max(1.0, np.abs(g["f_simple"]).max())
+
+
+@pytest.mark.parametrize("tag,n", [("g1_n128", 128), ("g1_n2048", 2048)])
+def test_direct_vs_reference_engines_fp32(tag, n):
+    g = load_golden_npz(tag, "f32")
+    f = run_direct(g["y"], g["mass"], precision="f32")
+    assert np.array_equal(f[:3 * n], g["y"][3 * n:])
+    assert rel_err_per_body(f, g["f_openmp"], n) <= TOL32
+
+
+def test_direct_n16_golden_state(oracle64):
+    """N = 16 (the solver golden state): not a multiple of any tile size."""
+    from oracle.oracle import load_table
+    y, m = load_table(golden_path("initial_state.txt"))
+    f = run_direct(y, m)
+    assert rel_err_per_body(f, oracle64.fcompute_openmp(y, m), 16) <= TOL64
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 129, 1000])
+def test_direct_ragged_sizes(oracle64, n):
+    rng = np.random.RandomState(n)
+    y = rng.uniform(-10, 10, 6 * n)
+    m = rng.uniform(0.1, 2.0, n)
+    f = run_direct(y, m)
+    ref = oracle64.fcompute_openmp(y, m)
+    if n == 1:
+        assert np.all(f[3:] == 0)
+    else:
+        assert rel_err_per_body(f, ref, n) <= TOL64
+
+
+def test_direct_coincident_bodies_use_min_distance(oracle64):
+    """r^2 < 1e-8 is clamped to 1e-8 (nbody_data.cpp:39-42); coincident bodies contribute exactly 0."""
+    y = np.zeros(6 * 4)
+    y[0:4] = [0.0, 0.0, 5e-5, 1.0]          # bodies 0 and 1 coincide; body 2 is 5e-5 away (r^2 = 2.5e-9 < 1e-8)
+    m = np.array([1.0, 2.0, 3.0, 4.0])
+    f = run_direct(y, m)
+    ref = oracle64.fcompute_openmp(y, m)
+    assert np.all(np.isfinite(f))
+    assert np.allclose(f, ref, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("ipt,segments", [(1, 1), (2, 3), (4, 1), (4, 16)])
+def test_direct_all_kernel_shapes(ipt, segments):
+    """Every (targets per thread) x (source segments) shape gives the same physics; shape (4, 1) writes f directly."""
+    g = load_golden_npz("g1_n2048")
+    f = run_direct(g["y"], g["mass"], options=(("direct_targets_per_thread", ipt), ("direct_segments", segments)))
+    assert rel_err_per_body(f, g["f_openmp"], 2048) <= TOL64
+    assert np.array_equal(f[:3 * 2048], g["y"][3 * 2048:])
+
+
+def test_direct_is_deterministic():
+    g = load_golden_npz("g1_n2048")
+    a = run_direct(g["y"], g["mass"])
+    b = run_direct(g["y"], g["mass"])
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0"])
+def test_direct_sharded_lanes_equal_single(devices):
+    """The reference's duplicate-device trick (test_nbody_engine.cpp:1259-1267): body-sharded lanes on one GPU.
+    Its gate for cuda vs multi-device cuda is 1e-15; shards sum the same sources in the same order."""
+    g = load_golden_npz("g1_n2048")
+    one = run_direct(g["y"], g["mass"], options=(("direct_segments", 4), ("direct_targets_per_thread", 1)))
+    many = run_direct(g["y"], g["mass"], devices=devices, options=(("direct_segments", 4), ("direct_targets_per_thread", 1)))
+    assert np.array_equal(one, many)
+
+
+def test_direct_c2_n65536_sampled(oracle64):
+    """BASELINE config C2 (N = 65,536): GPU result vs the oracle on a 256-body sample incl. both central bodies."""
+    n = 65536
+    y, m = universe(n)
+    f = run_direct(y, m).reshape(6, n)
+    t = np.unique(np.concatenate([[0, n // 2, n - 1], np.random.RandomState(3).randint(0, n, 253)]))
+    ref = oracle64.accel_subset(y, m, t)
+    assert rel_err_per_body(f[3:, t], ref, t.size) <= TOL64
+    ld = oracle64.accel_subset(y, m, t, long_double=True)
+    assert rel_err_per_body(f[3:, t], ld, t.size) <= TOL64
+    assert np.array_equal(f[:3].reshape(-1), y[3 * n:])
+
+
+def test_direct_c3_n1m_sampled_and_momentum(oracle64):
+    """BASELINE config C3 (N = 1,048,576): 64-body sample vs the oracle, plus a size-independent property:
+    total force sum_i m_i a_i = 0 (Newton's third law) to rounding."""
+    n = 1 << 20
+    y, m = universe(n)
+    f = run_direct(y, m).reshape(6, n)
+    t = np.unique(np.concatenate([[0, n // 2], np.random.RandomState(5).randint(0, n, 62)]))
+    ref = oracle64.accel_subset(y, m, t)
+    assert rel_err_per_body(f[3:, t], ref, t.size) <= TOL64
+    force = (f[3:] * m[None, :]).sum(axis=1)
+    scale = np.abs(f[3:] * m[None, :]).sum(axis=1)
+    assert np.all(np.abs(force) <= 1e-10 * scale)
