@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--ratio", type=float, default=10.0, help="Barnes-Hut distance_to_node_radius_ratio")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine tunable name=value (nb200_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -236,6 +237,9 @@ def run_nb200(args):
     eng = Engine(precision=precision, devices=[local], rank=rank, nranks=world, uid=uid,
                  kind="direct" if direct else "bh", distance_to_node_radius_ratio=args.ratio,
                  tree_layout="heap_stackless", tree_build_rate=0)
+    for item in args.opt:
+        k, v = item.split("=")
+        eng.set_option(k, int(v))
     if not eng.init(y, m):
         raise SystemExit("engine init failed: " + eng.last_error())
     ybuf = eng.get_y()

@@ -16,6 +16,8 @@
 //     pair feeds IPT pair interactions (i-blocking);
 //   * r^-3 comes from MUFU.RSQ64H + one cubically convergent correction
 //     (17 FP64-pipe instructions per pair, no sqrt, no divide, no slow path);
+//     the MinDistance clamp costs one integer min per pair: a tile is only redone with the
+//     exact clamp when some pair of it could be closer than sqrt(MinDistance);
 //   * the grid is (target blocks) x (source segments): splitting the source
 //     range makes the number of equal-sized work items >> 148 SMs for every N
 //     (N = 16 ... 4M, 1 ... 8 shards), partial sums are combined in a fixed
@@ -28,6 +30,9 @@
 #define NB200_DIRECT_THREADS 128
 #define NB200_DIRECT_TILE 128     // bodies per shared-memory tile
 #define NB200_DIRECT_STAGES 3
+#ifndef NB200_DIRECT_MINB
+#define NB200_DIRECT_MINB 2
+#endif
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX ISA 8.x, sm_90+) ---------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -67,7 +72,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 }
 
 // ---- one pair interaction --------------------------------------------------
+// r2^-3/2 from a ~20-bit seed y0 (MUFU.RSQ64H) and one cubically convergent correction:
+//   e = 1 - r2*y0^2;  r2^-1/2 = y0 (1-e)^-1/2 = y0 (1 + e/2 + 3e^2/8) + O(e^3) ~ 2^-60
+// 17 FP64-pipe instructions per pair: 3 DADD, DMUL + 2 DFMA (r2), 5 (refinement), 3 DMUL (m y^3), 3 DFMA.
 #if NB200_PRECISION == 2
+#define NB200_MIN_DISTANCE_HI 0x3E45798E	// high word of 1e-8 (0x3E45798EE2308C3A)
+
+// Exact form: r2 = max(r2, MinDistance) done on the integer pipe (r2 >= +0, so IEEE bit patterns order
+// like signed integers), which keeps the FP64 pipe for arithmetic.
 __device__ __forceinline__ void pair_interaction(double xi, double yi, double zi, const body4& s,
 												 double& ax, double& ay, double& az)
 {
@@ -75,14 +87,10 @@ __device__ __forceinline__ void pair_interaction(double xi, double yi, double zi
 	double	dy = s.y - yi;
 	double	dz = s.z - zi;
 	double	r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-	// r2 = max(r2, MinDistance) on the integer pipe: r2 >= +0, so the IEEE bit
-	// patterns order like signed integers (keeps the FP64 pipe for arithmetic).
 	long long		bits = __double_as_longlong(r2);
 	const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8
 	bits = bits < min_bits ? min_bits : bits;
 	r2 = __longlong_as_double(bits);
-	// y0 ~ r2^-1/2 to ~2^-20 (MUFU.RSQ64H); e = 1 - r2*y0^2;
-	// r2^-1/2 = y0 (1-e)^-1/2 = y0 (1 + e/2 + 3e^2/8) + O(e^3) ~ 2^-60.
 	double	y0;
 	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
 	double	h = r2 * y0;
@@ -94,6 +102,84 @@ __device__ __forceinline__ void pair_interaction(double xi, double yi, double zi
 	ax = fma(dx, c, ax);
 	ay = fma(dy, c, ay);
 	az = fma(dz, c, az);
+}
+
+// Fast form for the common case "no pair of this tile is closer than sqrt(MinDistance)": no clamp; instead one
+// integer min per pair tracks the smallest high word of r2 seen, and the caller redoes the tile with the exact
+// form if that minimum could be below MinDistance (self pair, bodies closer than 1e-4). The seed keeps the
+// low word of a dead temporary instead of a zeroed one (saves a move; it perturbs y0 by < 2^-20, which the
+// correction absorbs because e is computed from the y0 actually used).
+__device__ __forceinline__ void pair_interaction_fast(double xi, double yi, double zi, const body4& s,
+													  double& ax, double& ay, double& az, int& min_hi)
+{
+	double	dx = s.x - xi;
+	double	dy = s.y - yi;
+	double	dz = s.z - zi;
+	double	t1 = dx * dx;
+	double	r2 = fma(dz, dz, fma(dy, dy, t1));
+	min_hi = min(min_hi, __double2hiint(r2));
+	double	seed;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(r2));
+	double	y0 = __hiloint2double(__double2hiint(seed), __double2loint(t1));
+	double	h = r2 * y0;
+	double	e = fma(-h, y0, 1.0);
+	double	p = fma(e, 0.375, 0.5);
+	double	q = y0 * e;
+	double	y = fma(q, p, y0);
+	double	c = (y * y) * (s.m * y);
+	ax = fma(dx, c, ax);
+	ay = fma(dy, c, ay);
+	az = fma(dz, c, az);
+}
+
+// All pairs of one shared-memory tile for this thread's IPT targets, added to (ax, ay, az).
+template<int IPT>
+__device__ __forceinline__ void tile_interactions(const body4* __restrict__ tb, const real (&xi)[IPT], const real (&yi)[IPT],
+												  const real (&zi)[IPT], real (&ax)[IPT], real (&ay)[IPT], real (&az)[IPT])
+{
+	real	tx[IPT], ty[IPT], tz[IPT];
+	int		min_hi = 0x7fffffff;
+#pragma unroll
+	for(int k = 0; k < IPT; ++k)
+	{
+		tx[k] = ty[k] = tz[k] = 0;
+	}
+#pragma unroll 4
+	for(int j = 0; j < NB200_DIRECT_TILE; ++j)
+	{
+		const body4	s = tb[j];	// warp-uniform address: broadcast LDS.128 x2
+#pragma unroll
+		for(int k = 0; k < IPT; ++k)
+		{
+			pair_interaction_fast(xi[k], yi[k], zi[k], s, tx[k], ty[k], tz[k], min_hi);
+		}
+	}
+	if(min_hi <= NB200_MIN_DISTANCE_HI)
+	{
+		// rare: some r2 of this tile may be below MinDistance -> discard and redo with the exact clamp
+#pragma unroll
+		for(int k = 0; k < IPT; ++k)
+		{
+			tx[k] = ty[k] = tz[k] = 0;
+		}
+#pragma unroll 1
+		for(int j = 0; j < NB200_DIRECT_TILE; ++j)
+		{
+			const body4	s = tb[j];
+#pragma unroll
+			for(int k = 0; k < IPT; ++k)
+			{
+				pair_interaction(xi[k], yi[k], zi[k], s, tx[k], ty[k], tz[k]);
+			}
+		}
+	}
+#pragma unroll
+	for(int k = 0; k < IPT; ++k)
+	{
+		ax[k] += tx[k];
+		ay[k] += ty[k];
+		az[k] += tz[k];
+	}
 }
 #else
 __device__ __forceinline__ void pair_interaction(float xi, float yi, float zi, const body4& s,
@@ -109,6 +195,22 @@ __device__ __forceinline__ void pair_interaction(float xi, float yi, float zi, c
 	ax = fmaf(dx, c, ax);
 	ay = fmaf(dy, c, ay);
 	az = fmaf(dz, c, az);
+}
+
+template<int IPT>
+__device__ __forceinline__ void tile_interactions(const body4* __restrict__ tb, const real (&xi)[IPT], const real (&yi)[IPT],
+												  const real (&zi)[IPT], real (&ax)[IPT], real (&ay)[IPT], real (&az)[IPT])
+{
+#pragma unroll 4
+	for(int j = 0; j < NB200_DIRECT_TILE; ++j)
+	{
+		const body4	s = tb[j];	// warp-uniform address: broadcast LDS.128
+#pragma unroll
+		for(int k = 0; k < IPT; ++k)
+		{
+			pair_interaction(xi[k], yi[k], zi[k], s, ax[k], ay[k], az[k]);
+		}
+	}
 }
 #endif
 
@@ -133,7 +235,7 @@ __global__ void __launch_bounds__(256) direct_pack(const real* __restrict__ y, c
 // out: segments == 1 -> f (acc rows at 3n,4n,5n; velocity rows copied to 0..3n)
 //      segments  > 1 -> partial[seg][3][n_shard]
 template<int IPT>
-__global__ void __launch_bounds__(NB200_DIRECT_THREADS)
+__global__ void __launch_bounds__(NB200_DIRECT_THREADS, NB200_DIRECT_MINB)
 direct_pairs(const body4* __restrict__ src, const real* __restrict__ y, real* __restrict__ out,
 			 size_t n_shard, size_t shard_first, int n_tiles, int tiles_per_seg, int write_f)
 {
@@ -193,17 +295,7 @@ direct_pairs(const body4* __restrict__ src, const real* __restrict__ y, real* __
 			}
 		}
 		mbar_wait(&full[stage], (t / NB200_DIRECT_STAGES) & 1);
-		const body4*	tb = &tile[stage][0];
-#pragma unroll 4
-		for(int j = 0; j < NB200_DIRECT_TILE; ++j)
-		{
-			const body4	s = tb[j];	// warp-uniform address: broadcast LDS.128 (x2 for FP64)
-#pragma unroll
-			for(int k = 0; k < IPT; ++k)
-			{
-				pair_interaction(xi[k], yi[k], zi[k], s, ax[k], ay[k], az[k]);
-			}
-		}
+		tile_interactions<IPT>(&tile[stage][0], xi, yi, zi, ax, ay, az);
 		__syncthreads();
 	}
 

@@ -10,7 +10,7 @@ from util import universe
 pytestmark = pytest.mark.gpu
 
 TOL64 = 1e-12
-TOL32 = 2e-5
+TOL32 = 1e-4     # vs the reference's own FP32 result, whose sequential FP32 sum carries ~1e-5 of noise itself
 
 
 def run_direct(y, m, precision="f64", devices="0", options=()):
@@ -41,11 +41,16 @@ def test_direct_vs_reference_engines_fp64(tag, n):
 
 
 @pytest.mark.parametrize("tag,n", [("g1_n128", 128), ("g1_n2048", 2048)])
-def test_direct_vs_reference_engines_fp32(tag, n):
+def test_direct_vs_reference_engines_fp32(oracle64, tag, n):
     g = load_golden_npz(tag, "f32")
     f = run_direct(g["y"], g["mass"], precision="f32")
     assert np.array_equal(f[:3 * n], g["y"][3 * n:])
     assert rel_err_per_body(f, g["f_openmp"], n) <= TOL32
+    # against FP64 arithmetic on the same FP32 inputs the GPU result is at least as accurate as the reference's
+    truth = oracle64.fcompute_openmp(g["y"].astype(np.float64), g["mass"].astype(np.float64))
+    err_gpu = rel_err_per_body(f, truth, n)
+    err_ref = rel_err_per_body(g["f_openmp"], truth, n)
+    assert err_gpu <= max(2 * err_ref, 2e-6), (err_gpu, err_ref)
 
 
 def test_direct_n16_golden_state(oracle64):
