@@ -1,17 +1,650 @@
-// nb200 -- Barnes-Hut (kd-heap build, node update, tree walk). Filled in below.
+// nb200 -- Barnes-Hut on the device: kd-heap build, bottom-up node update, tree walk.
+//
+// Node layout is the reference's implicit binary heap (nbody/nbody_space_heap.cpp,
+// nbody_space_heap_func_priv.h): root = 1, children 2i / 2i+1, leaves [N, 2N), N = 2^k;
+// per node {mass centre xyz, radius_sqr} (one 32/16-byte vector, as cuda_bh_tex packs it,
+// nbody_engine_cuda_bh_tex.cpp:95-125), node mass, and for leaves the body index.
+//
+// What the reference does on the CPU every fcompute (D2H, std::nth_element recursion with OpenMP
+// tasks, repack, H2D; nbody_engine_cuda_bh_tex.cpp:79-126) happens here on the GPU:
+//
+//   build   The set split at every node is value-determined (left = the count/2 smallest along
+//           dim = depth % 3), so the leaf order can be produced without recursion:
+//           phase A  three global presorts (x, y, z) + one stable binary partition per level and
+//                    per ordering, done with an analytic segment base (segments are aligned
+//                    powers of two and every segment sends exactly half of its bodies left),
+//                    while segments are larger than NB200_BH_LOCAL bodies;
+//           phase B  one CTA per NB200_BH_LOCAL-body segment finishes the remaining levels in
+//                    shared memory with per-level bitonic sorts.
+//           Ties (equal coordinates across a median) are broken by body index; the reference's
+//           choice there is whatever std::nth_element happens to do.
+//   update  leaves, then one launch per level bottom-up (kupdate_node_bh_tex,
+//           nbody_engine_cuda_impl.cu:644-714), top 256 nodes in one CTA.
+//   walk    warp-coherent stackless walk (default): the 32 targets of a warp are consecutive
+//           leaves (a compact cell of the kd-order), the warp walks the UNION of their
+//           traversals with a warp-uniform `curr`, so each node is one broadcast load instead
+//           of 32 divergent ones. A lane that accepts a node sleeps until curr reaches that
+//           node's skip_idx; every lane therefore accepts exactly the nodes, in exactly the
+//           order, of its own nbody_space_heap_stackless::traverse
+//           (nbody_space_heap_stackless.cpp:3-28) -- results are bit-identical to the
+//           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape).
+//
+// The only library primitive is cub::DeviceRadixSort / DeviceSelect (3 presorts per rebuild and
+// the own-leaf compaction when the walk is sharded); everything else is hand-written.
 #ifndef NB200_BH_CUH
 #define NB200_BH_CUH
+
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include "nb200_common.cuh"
-struct bh_state { int dummy; };
-static void bh_free(bh_state* s) { delete s; }
-static int bh_fcompute(nb200_ctx*, nb200_lane&, const real*, real*, size_t, int&, std::string& err)
-{
-	err = "not built yet";
-	return NB200_ERR_UNSUPPORTED;
-}
-static int bh_export(nb200_ctx*, nb200_lane&, real*, real*, int*, std::string& err)
-{
-	err = "not built yet";
-	return NB200_ERR_UNSUPPORTED;
-}
+#include "nb200_direct.cuh"
+
+#define NB200_BH_LOCAL 1024        // bodies per phase-B segment (one CTA)
+#define NB200_BH_PART_BLOCK 1024   // elements per partition block (256 threads x 4)
+
+#if NB200_PRECISION == 2
+typedef double4 node4;	// 32 bytes
+#else
+typedef float4 node4;	// 16 bytes
 #endif
+
+struct bh_state
+{
+	size_t	n = 0;
+	int		log2n = 0;
+	node4*	xyzr = nullptr;		// [2n]
+	real*	nmass = nullptr;	// [2n]
+	real*	bmin = nullptr;		// [2n][3]
+	real*	bmax = nullptr;		// [2n][3]
+	int*	body_n = nullptr;	// [2n]
+	// build scratch
+	real*	keys_in = nullptr;
+	real*	keys_out = nullptr;
+	int*	iota = nullptr;
+	int*	ord[3] = {nullptr, nullptr, nullptr};
+	int*	ord_tmp[3] = {nullptr, nullptr, nullptr};
+	unsigned char*	side = nullptr;
+	unsigned*	blk = nullptr;	// [3][n / PART_BLOCK + 1]
+	void*	cub_tmp = nullptr;
+	size_t	cub_bytes = 0;
+	// sharded walk
+	int*	own_leaf = nullptr;	// leaves whose body belongs to this shard, ascending leaf order
+	unsigned char*	own_flag = nullptr;
+	int*	own_count = nullptr;
+	bool	have_tree = false;
+	real	built_ratio = 0;
+};
+
+static void bh_free(bh_state* s)
+{
+	if(s == nullptr) { return; }
+	void* ptrs[] = {s->xyzr, s->nmass, s->bmin, s->bmax, s->body_n, s->keys_in, s->keys_out, s->iota, s->ord[0], s->ord[1],
+					s->ord[2], s->ord_tmp[0], s->ord_tmp[1], s->ord_tmp[2], s->side, s->blk, s->cub_tmp, s->own_leaf,
+					s->own_flag, s->own_count};
+	for(void* p : ptrs)
+	{
+		if(p != nullptr) { cudaFree(p); }
+	}
+	delete s;
+}
+
+// ---- heap index algebra (nbody_space_heap_func_priv.h:34-72, CUDA branch :37-38) ----------------
+__device__ __forceinline__ int heap_skip_idx(int idx)
+{
+	return (idx >> (__ffs(~idx) - 1)) + 1;
+}
+__device__ __forceinline__ int heap_next_up(int idx, int tree_size)
+{
+	int left = idx << 1;
+	return left < tree_size ? left : heap_skip_idx(idx);
+}
+
+// ---- build, phase A -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bh_extract_keys(const body4* __restrict__ src, real* __restrict__ keys,
+													   int* __restrict__ iota, int n, int dim)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) { return; }
+	const body4 b = src[i];
+	keys[i] = dim == 0 ? b.x : (dim == 1 ? b.y : b.z);
+	iota[i] = i;
+}
+
+// side[body] = 1 if the body's rank inside its segment (along the split dimension) is in the upper half
+__global__ void __launch_bounds__(256) bh_mark_side(const int* __restrict__ ord_c, unsigned char* __restrict__ side, int n, int seg)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) { return; }
+	side[ord_c[i]] = ((i & (seg - 1)) >= (seg >> 1)) ? 1 : 0;
+}
+
+// blk[a][b] = number of left-going bodies among positions [b*PART_BLOCK, (b+1)*PART_BLOCK) of ordering a
+__global__ void __launch_bounds__(256) bh_part_count(const int* __restrict__ o0, const int* __restrict__ o1,
+													  const unsigned char* __restrict__ side, unsigned* __restrict__ blk, int nblk)
+{
+	const int* ord = blockIdx.y == 0 ? o0 : o1;
+	int base = blockIdx.x * NB200_BH_PART_BLOCK + threadIdx.x * 4;
+	int4 b = *reinterpret_cast<const int4*>(ord + base);
+	unsigned lefts = (side[b.x] == 0) + (side[b.y] == 0) + (side[b.z] == 0) + (side[b.w] == 0);
+	typedef cub::BlockReduce<unsigned, 256> reduce_t;
+	__shared__ typename reduce_t::TempStorage tmp;
+	unsigned total = reduce_t(tmp).Sum(lefts);
+	if(threadIdx.x == 0) { blk[blockIdx.y * (nblk + 1) + blockIdx.x] = total; }
+}
+
+// exclusive scan of each row of blk (nblk <= 4096 entries), one CTA per row
+__global__ void __launch_bounds__(1024) bh_part_scan(unsigned* __restrict__ blk, int nblk)
+{
+	unsigned* row = blk + blockIdx.x * (nblk + 1);
+	typedef cub::BlockScan<unsigned, 1024> scan_t;
+	__shared__ typename scan_t::TempStorage tmp;
+	__shared__ unsigned carry;
+	if(threadIdx.x == 0) { carry = 0; }
+	__syncthreads();
+	for(int b0 = 0; b0 < nblk; b0 += 1024)
+	{
+		int		i = b0 + threadIdx.x;
+		unsigned v = i < nblk ? row[i] : 0, ex, total;
+		scan_t(tmp).ExclusiveSum(v, ex, total);
+		if(i < nblk) { row[i] = ex + carry; }
+		__syncthreads();
+		if(threadIdx.x == 0) { carry += total; }
+		__syncthreads();
+	}
+}
+
+// stable partition of every seg-sized segment of two orderings: left-goers keep their order in the lower half
+__global__ void __launch_bounds__(256) bh_part_scatter(const int* __restrict__ o0, const int* __restrict__ o1,
+														int* __restrict__ d0, int* __restrict__ d1,
+														const unsigned char* __restrict__ side, const unsigned* __restrict__ blk,
+														int nblk, int seg)
+{
+	const int*	ord = blockIdx.y == 0 ? o0 : o1;
+	int*		dst = blockIdx.y == 0 ? d0 : d1;
+	int			base = blockIdx.x * NB200_BH_PART_BLOCK + threadIdx.x * 4;
+	int4		b = *reinterpret_cast<const int4*>(ord + base);
+	int			body[4] = {b.x, b.y, b.z, b.w};
+	unsigned	left[4], lefts = 0;
+#pragma unroll
+	for(int q = 0; q < 4; ++q)
+	{
+		left[q] = side[body[q]] == 0;
+		lefts += left[q];
+	}
+	typedef cub::BlockScan<unsigned, 256> scan_t;
+	__shared__ typename scan_t::TempStorage tmp;
+	unsigned before;
+	scan_t(tmp).ExclusiveSum(lefts, before);
+	before += blk[blockIdx.y * (nblk + 1) + blockIdx.x];	// left-goers before this thread's first element, globally
+#pragma unroll
+	for(int q = 0; q < 4; ++q)
+	{
+		int			i = base + q;
+		int			s0 = i & ~(seg - 1);
+		unsigned	in_seg_left = before - static_cast<unsigned>(s0 >> 1);	// every earlier segment sent exactly half left
+		int			d = left[q] ? s0 + static_cast<int>(in_seg_left)
+								: s0 + (seg >> 1) + (i - s0) - static_cast<int>(in_seg_left);
+		dst[d] = body[q];
+		before += left[q];
+	}
+}
+
+// ---- build, phase B: finish one segment of `local` bodies in shared memory ---------------------------
+template<int LOCAL_MAX>
+__global__ void __launch_bounds__(LOCAL_MAX / 2) bh_local_build(const body4* __restrict__ src, const int* __restrict__ ord,
+																 int* __restrict__ body_n, int n, int local, int first_depth)
+{
+	__shared__ real	coord[3][LOCAL_MAX];
+	__shared__ int	id[LOCAL_MAX];
+	__shared__ short perm[LOCAL_MAX];
+	const int seg0 = blockIdx.x * local;
+	for(int t = threadIdx.x; t < local; t += blockDim.x)
+	{
+		int body = ord != nullptr ? ord[seg0 + t] : seg0 + t;
+		const body4 b = src[body];
+		coord[0][t] = b.x;
+		coord[1][t] = b.y;
+		coord[2][t] = b.z;
+		id[t] = body;
+		perm[t] = static_cast<short>(t);
+	}
+	__syncthreads();
+	int depth = first_depth;
+	for(int seg = local; seg >= 2; seg >>= 1, ++depth)
+	{
+		const real* key = coord[depth % 3];
+		// bitonic sort of every aligned `seg`-block, ascending by (key, body index)
+		for(int k = 2; k <= seg; k <<= 1)
+		{
+			for(int j = k >> 1; j > 0; j >>= 1)
+			{
+				for(int t = threadIdx.x; t < local / 2; t += blockDim.x)
+				{
+					int		i = ((t & ~(j - 1)) << 1) | (t & (j - 1));	// lower index of the pair
+					int		p = i | j;
+					bool	up = (k == seg) || ((i & k) == 0);
+					short	a = perm[i], c = perm[p];
+					real	ka = key[a], kc = key[c];
+					bool	a_gt_c = ka > kc || (ka == kc && id[a] > id[c]);
+					if(a_gt_c == up)
+					{
+						perm[i] = c;
+						perm[p] = a;
+					}
+				}
+				__syncthreads();
+			}
+		}
+	}
+	for(int t = threadIdx.x; t < local; t += blockDim.x)
+	{
+		body_n[n + seg0 + t] = id[perm[t]];
+	}
+}
+
+// ---- node update --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bh_update_leaves(const body4* __restrict__ src, const int* __restrict__ body_n,
+														 node4* __restrict__ xyzr, real* __restrict__ nmass,
+														 real* __restrict__ bmin, real* __restrict__ bmax, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) { return; }
+	int			idx = n + i;
+	const body4	b = src[body_n[idx]];
+	node4		v;
+	v.x = b.x; v.y = b.y; v.z = b.z; v.w = 0;	// leaf: radius_sqr = 0 (value-initialised in the reference)
+	xyzr[idx] = v;
+	nmass[idx] = b.m;
+	bmin[3 * idx + 0] = b.x; bmin[3 * idx + 1] = b.y; bmin[3 * idx + 2] = b.z;
+	bmax[3 * idx + 0] = b.x; bmax[3 * idx + 1] = b.y; bmax[3 * idx + 2] = b.z;
+}
+
+// nbody_space_heap::update (nbody_space_heap.cpp:119-134)
+__device__ __forceinline__ void bh_update_node(int idx, node4* xyzr, real* nmass, real* bmin, real* bmax, real ratio_sqr)
+{
+	const int	l = idx << 1, r = l + 1;
+	const node4	cl = xyzr[l], cr = xyzr[r];
+	const real	ml = nmass[l], mr = nmass[r];
+	const real	m = ml + mr;
+	node4		v;
+	v.x = (cl.x * ml + cr.x * mr) / m;
+	v.y = (cl.y * ml + cr.y * mr) / m;
+	v.z = (cl.z * ml + cr.z * mr) / m;
+	real lo[3], hi[3];
+#pragma unroll
+	for(int d = 0; d < 3; ++d)
+	{
+		lo[d] = min(bmin[3 * l + d], bmin[3 * r + d]);
+		hi[d] = max(bmax[3 * l + d], bmax[3 * r + d]);
+		bmin[3 * idx + d] = lo[d];
+		bmax[3 * idx + d] = hi[d];
+	}
+	real ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+	real cx = (hi[0] + lo[0]) / 2 - v.x, cy = (hi[1] + lo[1]) / 2 - v.y, cz = (hi[2] + lo[2]) / 2 - v.z;
+	real rad = sqrt(ex * ex + ey * ey + ez * ez) * static_cast<real>(0.5) + sqrt(cx * cx + cy * cy + cz * cz);
+	v.w = (rad * rad) * ratio_sqr;
+	xyzr[idx] = v;
+	nmass[idx] = m;
+}
+
+__global__ void __launch_bounds__(256) bh_update_level(node4* xyzr, real* nmass, real* bmin, real* bmax, int level_size, real ratio_sqr)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= level_size) { return; }
+	bh_update_node(level_size + t, xyzr, nmass, bmin, bmax, ratio_sqr);
+}
+
+// levels of at most 256 nodes (the top of the tree), one CTA, block barrier between levels
+__global__ void __launch_bounds__(256) bh_update_top(node4* xyzr, real* nmass, real* bmin, real* bmax, int first_level_size, real ratio_sqr)
+{
+	for(int level = first_level_size; level >= 1; level >>= 1)
+	{
+		if(static_cast<int>(threadIdx.x) < level)
+		{
+			bh_update_node(level + threadIdx.x, xyzr, nmass, bmin, bmax, ratio_sqr);
+		}
+		__threadfence_block();
+		__syncthreads();
+	}
+}
+
+// ---- sharded walk: which leaves belong to this shard --------------------------------------------------------
+__global__ void __launch_bounds__(256) bh_flag_own(const int* __restrict__ body_n, unsigned char* __restrict__ flag, int n, int lo, int hi)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) { return; }
+	int b = body_n[n + i];
+	flag[i] = (b >= lo && b < hi) ? 1 : 0;
+}
+
+// ---- walk ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ node4 load_node(const node4* __restrict__ xyzr, int idx)
+{
+#if NB200_PRECISION == 2
+	// one 256-bit load per node (sm_100 LDG.E.256)
+	node4 v;
+	asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(xyzr + idx));
+	return v;
+#else
+	return __ldg(xyzr + idx);
+#endif
+}
+
+// accepted node -> same force form as the direct kernel (clamp applied after the acceptance test, as in
+// kfcompute_heap_bh_stackless, nbody_engine_cuda_impl.cu:399-413)
+__device__ __forceinline__ void node_force(real px, real py, real pz, const node4& nd, real m, real& ax, real& ay, real& az)
+{
+	body4 s;
+	s.x = nd.x; s.y = nd.y; s.z = nd.z; s.m = m;
+	pair_interaction(px, py, pz, s, ax, ay, az);
+}
+
+__device__ __forceinline__ void store_f(const real* __restrict__ y, real* __restrict__ f, size_t n_shard, size_t li,
+										real ax, real ay, real az)
+{
+	f[li] = y[3 * n_shard + li];
+	f[n_shard + li] = y[4 * n_shard + li];
+	f[2 * n_shard + li] = y[5 * n_shard + li];
+	f[3 * n_shard + li] = ax;
+	f[4 * n_shard + li] = ay;
+	f[5 * n_shard + li] = az;
+}
+
+// one thread per target, independent stackless walks (the reference kernel's shape)
+__global__ void __launch_bounds__(128) bh_walk_thread(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+													   const int* __restrict__ body_n, const int* __restrict__ own_leaf,
+													   const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
+													   size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= n_targets) { return; }
+	const int	leaf = n + (own_leaf != nullptr ? own_leaf[t] : t);
+	const int	tree_size = 2 * n;
+	const node4	me = load_node(xyzr, leaf);
+	real		ax = 0, ay = 0, az = 0;
+	unsigned	visits = 0, inter = 0;
+	int			curr = 1;
+	do
+	{
+		const node4	nd = load_node(xyzr, curr);
+		real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
+		real d2 = dx * dx + dy * dy + dz * dz;
+		++visits;
+		if(d2 > nd.w)
+		{
+			node_force(me.x, me.y, me.z, nd, nmass[curr], ax, ay, az);
+			++inter;
+			curr = heap_skip_idx(curr);
+		}
+		else
+		{
+			curr = heap_next_up(curr, tree_size);
+		}
+	} while(curr != 1);
+	store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
+	if(stats != nullptr)
+	{
+		atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
+		atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
+	}
+}
+
+// one warp per 32 consecutive targets, warp-uniform walk over the union of the lanes' traversals
+__global__ void __launch_bounds__(128) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+													 const int* __restrict__ body_n, const int* __restrict__ own_leaf,
+													 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
+													 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
+{
+	const int	t = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool	live = t < n_targets;
+	const int	tc = live ? t : n_targets - 1;	// idle lanes shadow the last target and never store
+	const int	leaf = n + (own_leaf != nullptr ? own_leaf[tc] : tc);
+	const int	tree_size = 2 * n;
+	const node4	me = load_node(xyzr, leaf);
+	real		ax = 0, ay = 0, az = 0;
+	unsigned	visits = 0, inter = 0;
+	int			curr = 1;		// warp-uniform
+	int			resume = 1;		// node at which this lane wakes up again (valid while asleep)
+	bool		awake = true;
+	do
+	{
+		const node4	nd = load_node(xyzr, curr);	// same address in every lane: one broadcast transaction
+		awake = awake || (curr == resume);
+		real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
+		real d2 = dx * dx + dy * dy + dz * dz;
+		const bool accept = awake && (d2 > nd.w);
+		const bool open = awake && !accept;
+		if(awake) { ++visits; }
+		if(__any_sync(0xffffffffu, accept))
+		{
+			const real m = nmass[curr];
+			if(accept)
+			{
+				node_force(me.x, me.y, me.z, nd, m, ax, ay, az);
+				++inter;
+				awake = false;
+				resume = heap_skip_idx(curr);
+			}
+		}
+		// descend if any awake lane needs the children (leaves have none: heap_next_up falls back to skip_idx)
+		curr = __any_sync(0xffffffffu, open) ? heap_next_up(curr, tree_size) : heap_skip_idx(curr);
+	} while(curr != 1);
+	if(live)
+	{
+		store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
+	}
+	if(stats != nullptr && live)
+	{
+		atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
+		atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
+	}
+}
+
+// ---- host orchestration ----------------------------------------------------------------------------------------------
+#define BH_CU(call)                                                                                    \
+	do                                                                                                 \
+	{                                                                                                  \
+		cudaError_t bh_res_ = (call);                                                                  \
+		if(bh_res_ != cudaSuccess)                                                                     \
+		{                                                                                              \
+			err = std::string(#call) + ": " + cudaGetErrorString(bh_res_);                            \
+			return NB200_ERR_CUDA;                                                                     \
+		}                                                                                              \
+	} while(0)
+
+static int bh_alloc(nb200_ctx* ctx, nb200_lane& l, std::string& err)
+{
+	const size_t n = ctx->n;
+	if(l.bh != nullptr && l.bh->n == n) { return NB200_OK; }
+	bh_free(l.bh);
+	l.bh = nullptr;
+	bh_state* s = new bh_state();
+	s->n = n;
+	while((static_cast<size_t>(1) << s->log2n) < n) { ++s->log2n; }
+	const size_t nblk = n / NB200_BH_PART_BLOCK + 1;
+	bool ok = cudaMalloc(&s->xyzr, 2 * n * sizeof(node4)) == cudaSuccess &&
+			  cudaMalloc(&s->nmass, 2 * n * sizeof(real)) == cudaSuccess &&
+			  cudaMalloc(&s->bmin, 6 * n * sizeof(real)) == cudaSuccess &&
+			  cudaMalloc(&s->bmax, 6 * n * sizeof(real)) == cudaSuccess &&
+			  cudaMalloc(&s->body_n, 2 * n * sizeof(int)) == cudaSuccess;
+	if(ok && n > NB200_BH_LOCAL)
+	{
+		ok = cudaMalloc(&s->keys_in, n * sizeof(real)) == cudaSuccess && cudaMalloc(&s->keys_out, n * sizeof(real)) == cudaSuccess &&
+			 cudaMalloc(&s->iota, n * sizeof(int)) == cudaSuccess && cudaMalloc(&s->side, n) == cudaSuccess &&
+			 cudaMalloc(&s->blk, 3 * nblk * sizeof(unsigned)) == cudaSuccess;
+		for(int a = 0; a < 3 && ok; ++a)
+		{
+			ok = cudaMalloc(&s->ord[a], n * sizeof(int)) == cudaSuccess && cudaMalloc(&s->ord_tmp[a], n * sizeof(int)) == cudaSuccess;
+		}
+		if(ok)
+		{
+			size_t bytes = 0;
+			cub::DeviceRadixSort::SortPairs(nullptr, bytes, s->keys_in, s->keys_out, s->iota, s->ord[0], static_cast<int>(n));
+			s->cub_bytes = bytes;
+		}
+	}
+	if(ok && ctx->nshards > 1)
+	{
+		size_t bytes = 0;
+		cub::DeviceSelect::Flagged(nullptr, bytes, thrust::counting_iterator<int>(0), s->own_flag, s->own_leaf, s->own_count, static_cast<int>(n));
+		s->cub_bytes = std::max(s->cub_bytes, bytes);
+		ok = cudaMalloc(&s->own_leaf, n * sizeof(int)) == cudaSuccess && cudaMalloc(&s->own_flag, n) == cudaSuccess &&
+			 cudaMalloc(&s->own_count, sizeof(int)) == cudaSuccess;
+	}
+	if(ok && s->cub_bytes > 0) { ok = cudaMalloc(&s->cub_tmp, s->cub_bytes) == cudaSuccess; }
+	if(!ok)
+	{
+		cudaGetLastError();
+		bh_free(s);
+		err = "tree allocation failed";
+		return NB200_ERR_ALLOC;
+	}
+	// slot 0 is unused by the heap; keep it defined for bh_export
+	cudaMemsetAsync(s->xyzr, 0, sizeof(node4), l.stream);
+	cudaMemsetAsync(s->nmass, 0, sizeof(real), l.stream);
+	cudaMemsetAsync(s->body_n, 0xff, n * sizeof(int), l.stream);	// TREE_NO_BODY for internal nodes
+	l.bh = s;
+	return NB200_OK;
+}
+
+// Leaf order (body_n[n..2n)) from the packed bodies in l.src.
+static int bh_build_topology(nb200_ctx* ctx, nb200_lane& l, int& launches, std::string& err)
+{
+	bh_state*	s = l.bh;
+	const int	n = static_cast<int>(s->n);
+	if(n == 1)
+	{
+		BH_CU(cudaMemsetAsync(s->body_n + 1, 0, sizeof(int), l.stream));
+		return NB200_OK;
+	}
+	if(n <= NB200_BH_LOCAL)
+	{
+		bh_local_build<NB200_BH_LOCAL><<<1, std::max(32, n / 2), 0, l.stream>>>(l.src, nullptr, s->body_n, n, n, 0);
+		++launches;
+		BH_CU(cudaGetLastError());
+		return NB200_OK;
+	}
+	const unsigned g256 = static_cast<unsigned>((n + 255) / 256);
+	for(int a = 0; a < 3; ++a)
+	{
+		bh_extract_keys<<<g256, 256, 0, l.stream>>>(l.src, s->keys_in, s->iota, n, a);
+		++launches;
+		size_t bytes = s->cub_bytes;
+		BH_CU(cub::DeviceRadixSort::SortPairs(s->cub_tmp, bytes, s->keys_in, s->keys_out, s->iota, s->ord[a], n, 0,
+											  static_cast<int>(sizeof(real) * 8), l.stream));
+	}
+	const int nblk = n / NB200_BH_PART_BLOCK;
+	int depth = 0;
+	for(int seg = n; seg > NB200_BH_LOCAL; seg >>= 1, ++depth)
+	{
+		const int c = depth % 3, a0 = (c + 1) % 3, a1 = (c + 2) % 3;
+		bh_mark_side<<<g256, 256, 0, l.stream>>>(s->ord[c], s->side, n, seg);
+		// the ordering along the split dimension is already partitioned (its lower half IS the left child)
+		bh_part_count<<<dim3(nblk, 2), 256, 0, l.stream>>>(s->ord[a0], s->ord[a1], s->side, s->blk, nblk);
+		bh_part_scan<<<2, 1024, 0, l.stream>>>(s->blk, nblk);
+		bh_part_scatter<<<dim3(nblk, 2), 256, 0, l.stream>>>(s->ord[a0], s->ord[a1], s->ord_tmp[a0], s->ord_tmp[a1], s->side,
+															   s->blk, nblk, seg);
+		launches += 4;
+		std::swap(s->ord[a0], s->ord_tmp[a0]);
+		std::swap(s->ord[a1], s->ord_tmp[a1]);
+	}
+	BH_CU(cudaGetLastError());
+	bh_local_build<NB200_BH_LOCAL><<<n / NB200_BH_LOCAL, NB200_BH_LOCAL / 2, 0, l.stream>>>(l.src, s->ord[depth % 3], s->body_n, n,
+																							NB200_BH_LOCAL, depth);
+	++launches;
+	BH_CU(cudaGetLastError());
+	return NB200_OK;
+}
+
+static int bh_update_geometry(nb200_ctx* ctx, nb200_lane& l, int& launches, std::string& err)
+{
+	bh_state*	s = l.bh;
+	const int	n = static_cast<int>(s->n);
+	const real	ratio_sqr = ctx->bh_ratio * ctx->bh_ratio;
+	bh_update_leaves<<<(n + 255) / 256, 256, 0, l.stream>>>(l.src, s->body_n, s->xyzr, s->nmass, s->bmin, s->bmax, n);
+	++launches;
+	int level = n >> 1;
+	for(; level > 256; level >>= 1)
+	{
+		bh_update_level<<<(level + 255) / 256, 256, 0, l.stream>>>(s->xyzr, s->nmass, s->bmin, s->bmax, level, ratio_sqr);
+		++launches;
+	}
+	if(level >= 1)
+	{
+		bh_update_top<<<1, 256, 0, l.stream>>>(s->xyzr, s->nmass, s->bmin, s->bmax, level, ratio_sqr);
+		++launches;
+	}
+	BH_CU(cudaGetLastError());
+	s->built_ratio = ctx->bh_ratio;
+	return NB200_OK;
+}
+
+static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, size_t step, int& launches, std::string& err)
+{
+	int rc = bh_alloc(ctx, l, err);
+	if(rc != NB200_OK) { return rc; }
+	bh_state*	s = l.bh;
+	const int	n = static_cast<int>(s->n);
+	// same rebuild rule as nbody_engine_cuda_bh_tex.cpp:76-77
+	const bool rebuild = ctx->bh_build_rate == 0 || !s->have_tree || (step % ctx->bh_build_rate) == 0;
+	if(rebuild)
+	{
+		rc = bh_build_topology(ctx, l, launches, err);
+		if(rc != NB200_OK) { return rc; }
+		if(ctx->nshards > 1)
+		{
+			const int lo = static_cast<int>(static_cast<size_t>(l.shard) * ctx->n_shard);
+			bh_flag_own<<<(n + 255) / 256, 256, 0, l.stream>>>(s->body_n, s->own_flag, n, lo, lo + static_cast<int>(ctx->n_shard));
+			size_t bytes = s->cub_bytes;
+			BH_CU(cub::DeviceSelect::Flagged(s->cub_tmp, bytes, thrust::counting_iterator<int>(0), s->own_flag, s->own_leaf,
+											 s->own_count, n, l.stream));
+			launches += 1;
+		}
+		s->have_tree = true;
+	}
+	rc = bh_update_geometry(ctx, l, launches, err);
+	if(rc != NB200_OK) { return rc; }
+	if(ctx->opt_timing) { BH_CU(cudaEventRecord(l.ev_t[2], l.stream)); }
+
+	unsigned long long* stats = nullptr;
+	if(ctx->bh_stats)
+	{
+		BH_CU(cudaMemsetAsync(l.d_scalar + 2, 0, 2 * sizeof(unsigned long long), l.stream));
+		stats = l.d_scalar;
+	}
+	const int	n_targets = static_cast<int>(ctx->n_shard);
+	const int*	own = ctx->nshards > 1 ? s->own_leaf : nullptr;
+	const int	shard_first = static_cast<int>(static_cast<size_t>(l.shard) * ctx->n_shard);
+	const int	block = 128;
+	const unsigned grid = static_cast<unsigned>((n_targets + block - 1) / block);
+	if(ctx->opt_walk_block == 1)
+	{
+		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+	}
+	else
+	{
+		bh_walk_warp<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+	}
+	++launches;
+	BH_CU(cudaGetLastError());
+	if(ctx->opt_timing)
+	{
+		BH_CU(cudaEventRecord(l.ev_t[3], l.stream));
+		BH_CU(cudaEventRecord(l.ev_t[4], l.stream));
+	}
+	return NB200_OK;
+}
+
+static int bh_export(nb200_ctx* ctx, nb200_lane& l, real* xyzr, real* mass, int* body_n, std::string& err)
+{
+	bh_state* s = l.bh;
+	const size_t ts = 2 * s->n;
+	if(xyzr != nullptr) { BH_CU(cudaMemcpyAsync(xyzr, s->xyzr, ts * sizeof(node4), cudaMemcpyDeviceToHost, l.stream)); }
+	if(mass != nullptr) { BH_CU(cudaMemcpyAsync(mass, s->nmass, ts * sizeof(real), cudaMemcpyDeviceToHost, l.stream)); }
+	if(body_n != nullptr) { BH_CU(cudaMemcpyAsync(body_n, s->body_n, ts * sizeof(int), cudaMemcpyDeviceToHost, l.stream)); }
+	BH_CU(cudaStreamSynchronize(l.stream));
+	(void)ctx;
+	return NB200_OK;
+}
+
+#endif // NB200_BH_CUH

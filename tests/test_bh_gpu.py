@@ -1,0 +1,168 @@
+"""Barnes-Hut on the GPU vs the reference's nbody_space_heap / simple_bh (tests/golden/*.npz, generated from
+oracle/_ref) and the CPU oracle: identical tree (leaf order exact, node data to rounding) and per-body
+acceleration <= 1e-12 relative, mirroring the cuda_bh_tex rows of test_nbody_engine.cpp:1227-1336."""
+import numpy as np
+import pytest
+
+from conftest import load_golden_npz, golden_path, rel_err_per_body
+from util import universe
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def run_bh(y, m, ratio, precision="f64", devices="0", layout="heap_stackless", rate=0, walk_mode=0, steps=1, stats=False):
+    """Returns list of f per step (y *= 0.99 between steps, like test_fcompute), the exported tree and stats."""
+    from nbody_b200 import Engine
+    out = []
+    with Engine(precision=precision, devices=devices, kind="bh", distance_to_node_radius_ratio=ratio,
+                tree_layout=layout, tree_build_rate=rate) as e:
+        e.set_option("walk_mode", walk_mode)
+        assert e.init(y, m)
+        if stats:
+            e.bh_walk_stats(True)
+        ybuf = e.create_buffer(e.get_y().size())
+        e.copy_buffer(ybuf, e.get_y())
+        f = e.create_buffer(e.get_y().size())
+        for step in range(steps):
+            e.fill_buffer(f, -1e10)
+            e.set_step(step)
+            e.fcompute(0.0, ybuf, f)
+            out.append(e.read_buffer(f))
+            e.fmadd_inplace(ybuf, ybuf, -0.01)
+        tree = e.bh_export_tree()
+        st = e.bh_walk_stats(True) if stats else None
+    return out, tree, st
+
+
+@pytest.mark.parametrize("tag,n,ratio,key", [("g1_n128", 128, 3.1623, "3p1623"), ("g1_n128", 128, 10.0, "10"),
+                                             ("g1_n256", 256, 3.1623, "3p1623"), ("g1_n256", 256, 10.0, "10"),
+                                             ("g1_n2048", 2048, 10.0, "10")])
+@pytest.mark.parametrize("layout", ["heap", "heap_stackless"])
+def test_bh_vs_reference_simple_bh(tag, n, ratio, key, layout):
+    g = load_golden_npz(tag)
+    (f,), (xyzr, mass, body), _ = run_bh(g["y"], g["mass"], ratio, layout=layout)
+    assert np.array_equal(body[n:], g["tree_body_" + key][n:])                 # same leaf order as nbody_space_heap::build
+    assert np.allclose(mass[1:], g["tree_mass_" + key][1:], rtol=1e-15, atol=0)
+    assert np.allclose(xyzr[1:, :3], g["tree_xyzr_" + key][1:, :3], rtol=1e-13, atol=1e-13)
+    assert np.allclose(xyzr[1:, 3], g["tree_xyzr_" + key][1:, 3], rtol=1e-11, atol=0)
+    assert np.array_equal(f[:3 * n], g["y"][3 * n:])
+    assert rel_err_per_body(f, g["f_bh_" + key], n) <= TOL
+
+
+def test_bh_huge_ratio_equals_direct():
+    """ratio 1e8 opens every internal node: BH == direct sum (reference gate 1e-11 absolute)."""
+    g = load_golden_npz("g1_n256")
+    (f,), _, st = run_bh(g["y"], g["mass"], 1e8, stats=True)
+    assert np.abs(f - g["f_simple"]).max() <= 1e-11
+    assert rel_err_per_body(f, g["f_bh_1e8"], 256) <= TOL
+    assert st[1] == 256 * 255
+
+
+def test_bh_walk_modes_bit_identical():
+    g = load_golden_npz("g1_n2048")
+    (a,), _, sa = run_bh(g["y"], g["mass"], 10.0, walk_mode=0, stats=True)
+    (b,), _, sb = run_bh(g["y"], g["mass"], 10.0, walk_mode=1, stats=True)
+    assert np.array_equal(a, b)
+    assert sa == sb and sa[0] > sa[1] > 0
+
+
+def test_bh_counts_match_oracle(oracle64):
+    g = load_golden_npz("g1_n2048")
+    t = oracle64.heap_build(g["y"], g["mass"], 10.0)
+    _, visits, inter = oracle64.fcompute_bh(g["y"], g["mass"], t)
+    _, _, st = run_bh(g["y"], g["mass"], 10.0, stats=True)
+    assert st == (visits, inter)
+
+
+@pytest.mark.parametrize("rate", [0, 2])
+def test_bh_tree_build_rate(oracle64, rate):
+    """tree_build_rate {0, 2} x 2 steps (test_nbody_engine.cpp:1283-1336): with rate 2 the second step only
+    refreshes the geometry of the step-0 topology -- compared with the oracle doing the same."""
+    g = load_golden_npz("g1_n256")
+    fs, _, _ = run_bh(g["y"], g["mass"], 3.1623, rate=rate, steps=3)
+    y = g["y"].copy()
+    tree = None
+    for step in range(3):
+        if rate == 0 or tree is None or step % rate == 0:
+            tree = oracle64.heap_build(y, g["mass"], 3.1623)
+        else:
+            tree = oracle64.heap_rebuild(tree, y)
+        want, _, _ = oracle64.fcompute_bh(y, g["mass"], tree)
+        assert rel_err_per_body(fs[step], want, 256) <= TOL, step
+        y = y + y * -0.01
+
+
+def test_bh_n16_golden_state(oracle64):
+    from oracle.oracle import load_table
+    y, m = load_table(golden_path("initial_state.txt"))
+    (f,), (xyzr, mass, body), _ = run_bh(y, m, 10.0)
+    t = oracle64.heap_build(y, m, 10.0)
+    assert np.array_equal(body[16:], t["body_n"][16:].astype(np.int32))
+    want, _, _ = oracle64.fcompute_bh(y, m, t)
+    assert rel_err_per_body(f, want, 16) <= TOL
+
+
+@pytest.mark.parametrize("n", [2, 4, 1024, 4096])
+def test_bh_small_and_boundary_sizes(oracle64, n):
+    """N = 1024 is the last single-CTA build, N = 4096 the first with two partition levels."""
+    rng = np.random.RandomState(n)
+    y = rng.uniform(-10, 10, 6 * n)
+    m = rng.uniform(0.1, 2.0, n)
+    (f,), (_, _, body), _ = run_bh(y, m, 2.0)
+    t = oracle64.heap_build(y, m, 2.0)
+    assert np.array_equal(body[n:], t["body_n"][n:].astype(np.int32))
+    want, _, _ = oracle64.fcompute_bh(y, m, t)
+    assert rel_err_per_body(f, want, n) <= TOL
+
+
+def test_bh_rejects_non_power_of_two():
+    from nbody_b200 import Engine
+    rng = np.random.RandomState(0)
+    with Engine(kind="bh") as e:
+        assert e.init(rng.rand(6 * 12), np.ones(12))
+        f = e.create_buffer(e.get_y().size())
+        e.fill_buffer(f, 7.0)
+        e.fcompute(0.0, e.get_y(), f)
+        assert np.all(e.read_buffer(f) == 7.0)
+        assert "power of two" in e.last_error()
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0"])
+def test_bh_sharded_lanes_equal_single(devices):
+    g = load_golden_npz("g1_n2048")
+    (one,), _, _ = run_bh(g["y"], g["mass"], 10.0)
+    (many,), _, _ = run_bh(g["y"], g["mass"], 10.0, devices=devices)
+    assert np.array_equal(one, many)
+
+
+def test_bh_fp32():
+    g = load_golden_npz("g1_n2048", "f32")
+    (f,), (_, _, body), _ = run_bh(g["y"], g["mass"], 10.0, precision="f32")
+    assert np.array_equal(body[2048:], g["tree_body_10"][2048:])
+    assert rel_err_per_body(f, g["f_bh_10"], 2048) <= 1e-4
+
+
+def test_bh_n65536_full_vs_oracle(oracle64):
+    """Phase-A build (6 partition levels) + walk at N = 65,536, ratio 3.1623, every body checked."""
+    n = 65536
+    y, m = universe(n)
+    (f,), (xyzr, mass, body), st = run_bh(y, m, 3.1623, stats=True)
+    t = oracle64.heap_build(y, m, 3.1623)
+    assert np.array_equal(body[n:], t["body_n"][n:].astype(np.int32))
+    assert np.allclose(xyzr[1:, :3], t["xyzr"][1:, :3], rtol=1e-12, atol=1e-12)
+    want, visits, inter = oracle64.fcompute_bh(y, m, t)
+    assert st == (visits, inter)
+    assert rel_err_per_body(f, want, n) <= TOL
+
+
+def test_bh_n1m_tree_equals_oracle_and_walk_ratio1(oracle64):
+    """N = 1,048,576: leaf order identical to the CPU nth_element build; walk at ratio 1 vs the oracle."""
+    n = 1 << 20
+    y, m = universe(n)
+    (f,), (_, _, body), st = run_bh(y, m, 1.0, stats=True)
+    t = oracle64.heap_build(y, m, 1.0)
+    assert np.array_equal(body[n:], t["body_n"][n:].astype(np.int32))
+    want, visits, inter = oracle64.fcompute_bh(y, m, t)
+    assert st == (visits, inter)
+    assert rel_err_per_body(f, want, n) <= TOL
