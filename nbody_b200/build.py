@@ -75,7 +75,11 @@ def build_adapter(precision, force=False):
     cmd = ["/usr/bin/g++", "-std=gnu++17", "-O2", "-fPIC", "-shared", "-fopenmp", "-w",
            "-DNB_COORD_PRECISION=%d" % PRECISIONS[precision], "-DNB200_PRECISION=%d" % PRECISIONS[precision],
            "-I" + os.path.join(ROOT, "oracle", "qtshim"), "-I" + REFERENCE, "-I" + os.path.join(ROOT, "include"),
-           "-o", out] + _sources(HOST, (".cpp",)) + ["-ldl"]
+           "-o", out] + _sources(HOST, (".cpp",)) + [
+               # base-class symbols come from the shim-built reference, kernels from libnb200
+               "-L" + os.path.join(ROOT, "oracle", "_ref"), "-lnbref_%s" % precision,
+               "-L" + CSRC, "-lnb200_%s" % precision,
+               "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-Wl,-rpath,$ORIGIN/../csrc", "-ldl"]
     subprocess.run(cmd, check=True)
     return out
 

@@ -1,0 +1,581 @@
+#include "nbody_engine_b200.h"
+
+#include <QDebug>
+#include <algorithm>
+
+#include "nb200.h"
+
+static_assert(sizeof(nb200_real) == sizeof(nbcoord_t), "libnb200 precision must match NB_COORD_PRECISION");
+
+class nbody_engine_b200::smemory : public nbody_engine::memory
+{
+	nb200_ctx*	m_ctx;
+	nb200_buf*	m_buf;
+	size_t		m_size;
+public:
+	smemory(nb200_ctx* ctx, size_t size) : m_ctx(ctx), m_buf(nullptr), m_size(0)
+	{
+		if(nb200_alloc(ctx, size, &m_buf) == NB200_OK)
+		{
+			m_size = size;
+		}
+	}
+	~smemory()
+	{
+		nb200_free(m_ctx, m_buf);
+	}
+	bool valid() const
+	{
+		return m_buf != nullptr;
+	}
+	nb200_buf* buf() const
+	{
+		return m_buf;
+	}
+	const nb200_ctx* owner() const
+	{
+		return m_ctx;
+	}
+	size_t size() const override
+	{
+		return m_size;
+	}
+};
+
+struct nbody_engine_b200::data
+{
+	e_force				m_force;
+	nbcoord_t			m_ratio;
+	size_t				m_tree_build_rate;
+	e_tree_layout		m_tree_layout;
+	std::vector<int>	m_device_ids;
+	nb200_ctx*			m_ctx;
+	smemory*			m_y;
+	nbody_data*			m_data;
+	data() : m_force(ef_direct), m_ratio(10), m_tree_build_rate(0), m_tree_layout(etl_heap_stackless),
+		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr)
+	{
+	}
+	//! memory -> C-ABI handle; NULL (after logging) for foreign or NULL memory, like the reference's dynamic_cast checks
+	nb200_buf* handle(const memory* m, const char* name) const
+	{
+		const smemory* s = dynamic_cast<const smemory*>(m);
+		if(s == nullptr || s->owner() != m_ctx)
+		{
+			qDebug() << name << "is not smemory";
+			return nullptr;
+		}
+		return s->buf();
+	}
+	void check(int rc, const char* what) const
+	{
+		if(rc != NB200_OK)
+		{
+			qDebug() << what << nb200_last_error(m_ctx);
+		}
+	}
+};
+
+nbody_engine_b200::nbody_engine_b200(e_force force, nbcoord_t distance_to_node_radius_ratio,
+									 size_t tree_build_rate, e_tree_layout tl) :
+	d(new data())
+{
+	d->m_force = force;
+	d->m_ratio = distance_to_node_radius_ratio;
+	d->m_tree_build_rate = tree_build_rate;
+	d->m_tree_layout = tl;
+}
+
+nbody_engine_b200::~nbody_engine_b200()
+{
+	delete d->m_y;
+	nb200_destroy(d->m_ctx);
+	delete d;
+}
+
+const char* nbody_engine_b200::type_name() const
+{
+	return d->m_force == ef_direct ? "nbody_engine_b200" : "nbody_engine_b200_bh";
+}
+
+bool nbody_engine_b200::ensure_context()
+{
+	if(d->m_ctx != nullptr)
+	{
+		return true;
+	}
+	int rc = nb200_create(&d->m_ctx, d->m_device_ids.data(), static_cast<int>(d->m_device_ids.size()), 0, 1, nullptr);
+	if(rc != NB200_OK)
+	{
+		qDebug() << "nb200_create failed" << rc;
+		d->m_ctx = nullptr;
+		return false;
+	}
+	if(d->m_force == ef_barnes_hut)
+	{
+		int layout = (d->m_tree_layout == etl_heap) ? NB200_TREE_HEAP : NB200_TREE_HEAP_STACKLESS;
+		d->check(nb200_bh_configure(d->m_ctx, d->m_ratio, layout, d->m_tree_build_rate), "nb200_bh_configure");
+	}
+	return true;
+}
+
+bool nbody_engine_b200::init(nbody_data* body_data)
+{
+	if(body_data == nullptr || body_data->get_count() == 0 || !ensure_context())
+	{
+		return false;
+	}
+	d->m_data = body_data;
+	size_t	count = body_data->get_count();
+	if(nb200_set_bodies(d->m_ctx, count, body_data->get_mass()) != NB200_OK)
+	{
+		qDebug() << "nb200_set_bodies" << nb200_last_error(d->m_ctx);
+		return false;
+	}
+	delete d->m_y;
+	d->m_y = dynamic_cast<smemory*>(create_buffer(sizeof(nbcoord_t) * problem_size()));
+	if(d->m_y == nullptr)
+	{
+		return false;
+	}
+	// AoS nbody_data -> [rx|ry|rz|vx|vy|vz] (nbody_engine_cuda.cpp:113-139)
+	std::vector<nbcoord_t>	ytmp(problem_size());
+	const nbvertex_t*		vrt = body_data->get_vertites();
+	const nbvertex_t*		vel = body_data->get_velosites();
+	for(size_t i = 0; i != count; ++i)
+	{
+		ytmp[i] = vrt[i].x;
+		ytmp[count + i] = vrt[i].y;
+		ytmp[2 * count + i] = vrt[i].z;
+		ytmp[3 * count + i] = vel[i].x;
+		ytmp[4 * count + i] = vel[i].y;
+		ytmp[5 * count + i] = vel[i].z;
+	}
+	write_buffer(d->m_y, ytmp.data());
+	return true;
+}
+
+void nbody_engine_b200::get_data(nbody_data* body_data)
+{
+	if(d->m_y == nullptr || body_data == nullptr)
+	{
+		return;
+	}
+	size_t					count = body_data->get_count();
+	std::vector<nbcoord_t>	ytmp(problem_size());
+	read_buffer(ytmp.data(), d->m_y);
+	nbvertex_t*				vrt = body_data->get_vertites();
+	nbvertex_t*				vel = body_data->get_velosites();
+	for(size_t i = 0; i != count; ++i)
+	{
+		vrt[i].x = ytmp[i];
+		vrt[i].y = ytmp[count + i];
+		vrt[i].z = ytmp[2 * count + i];
+		vel[i].x = ytmp[3 * count + i];
+		vel[i].y = ytmp[4 * count + i];
+		vel[i].z = ytmp[5 * count + i];
+	}
+}
+
+size_t nbody_engine_b200::problem_size() const
+{
+	return d->m_data != nullptr ? 6 * d->m_data->get_count() : 0;
+}
+
+nbody_engine::memory* nbody_engine_b200::get_y()
+{
+	return d->m_y;
+}
+
+// time and step live in nbody_data, as in every reference engine (nbody_engine_cuda.cpp:177-200)
+void nbody_engine_b200::advise_time(const nbcoord_t& dt)
+{
+	d->m_data->advise_time(dt);
+}
+
+nbcoord_t nbody_engine_b200::get_time() const
+{
+	return d->m_data->get_time();
+}
+
+void nbody_engine_b200::set_time(nbcoord_t t)
+{
+	d->m_data->set_time(t);
+}
+
+size_t nbody_engine_b200::get_step() const
+{
+	return d->m_data->get_step();
+}
+
+void nbody_engine_b200::set_step(size_t s)
+{
+	d->m_data->set_step(s);
+}
+
+void nbody_engine_b200::fcompute(const nbcoord_t& t, const memory* _y, memory* _f)
+{
+	Q_UNUSED(t);
+	nb200_buf*	y = d->handle(_y, "y");
+	if(y == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	f = d->handle(_f, "f");
+	if(f == nullptr)
+	{
+		return;
+	}
+	advise_compute_count();
+	if(d->m_force == ef_direct)
+	{
+		d->check(nb200_fcompute_direct(d->m_ctx, y, f), "fcompute");
+	}
+	else
+	{
+		d->check(nb200_fcompute_bh(d->m_ctx, y, f, get_step()), "fcompute");
+	}
+}
+
+void nbody_engine_b200::clamp(memory* _y, nbcoord_t b)
+{
+	nb200_buf*	y = d->handle(_y, "y");
+	if(y == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_clamp(d->m_ctx, y, b), "clamp");
+}
+
+nbody_engine::memory* nbody_engine_b200::create_buffer(size_t s)
+{
+	if(!ensure_context())
+	{
+		return nullptr;
+	}
+	smemory*	mem = new smemory(d->m_ctx, s);
+	if(!mem->valid())
+	{
+		delete mem;
+		return nullptr;
+	}
+	return mem;
+}
+
+void nbody_engine_b200::free_buffer(memory* mem)
+{
+	delete mem;
+}
+
+void nbody_engine_b200::read_buffer(void* dst, const memory* _src)
+{
+	nb200_buf*	src = d->handle(_src, "src");
+	if(src == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_read(d->m_ctx, dst, src), "read_buffer");
+}
+
+void nbody_engine_b200::write_buffer(memory* _dst, const void* src)
+{
+	nb200_buf*	dst = d->handle(_dst, "dst");
+	if(dst == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_write(d->m_ctx, dst, src), "write_buffer");
+}
+
+void nbody_engine_b200::copy_buffer(memory* _a, const memory* _b)
+{
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	b = d->handle(_b, "b");
+	if(b == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_copy(d->m_ctx, a, b), "copy_buffer");
+}
+
+void nbody_engine_b200::fill_buffer(memory* _a, const nbcoord_t& value)
+{
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_fill(d->m_ctx, a, value), "fill_buffer");
+}
+
+void nbody_engine_b200::fmadd_inplace(memory* _a, const memory* _b, const nbcoord_t& c)
+{
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	b = d->handle(_b, "b");
+	if(b == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_fmadd_inplace(d->m_ctx, a, b, c), "fmadd_inplace");
+}
+
+void nbody_engine_b200::fmadd(memory* _a, const memory* _b, const memory* _c, const nbcoord_t& _d)
+{
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	b = d->handle(_b, "b");
+	if(b == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	c = d->handle(_c, "c");
+	if(c == nullptr)
+	{
+		return;
+	}
+	d->check(nb200_fmadd(d->m_ctx, a, b, c, _d), "fmadd");
+}
+
+namespace {
+//! Handles of the first `count` buffers; entries that are not ours become NULL (the C ABI rejects them
+//! only when their coefficient is non-zero, exactly as the base-class loops would)
+std::vector<const nb200_buf*> handles(const nbody_engine::memory_array& arr, size_t count, const nb200_ctx* ctx)
+{
+	std::vector<const nb200_buf*>	h(std::max<size_t>(count, 1), nullptr);
+	for(size_t k = 0; k < count; ++k)
+	{
+		const nbody_engine_b200::smemory* s = dynamic_cast<const nbody_engine_b200::smemory*>(arr[k]);
+		h[k] = (s != nullptr && s->owner() == ctx) ? s->buf() : nullptr;
+	}
+	return h;
+}
+}  // namespace
+
+void nbody_engine_b200::fmaddn_inplace(memory* _a, const memory_array& _b, const nbcoord_t* c, size_t csize)
+{
+	if(c == NULL)
+	{
+		return;
+	}
+	if(csize > _b.size())
+	{
+		qDebug() << "csize > b.size()";
+		return;
+	}
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	std::vector<const nb200_buf*>	b(handles(_b, csize, d->m_ctx));
+	d->check(nb200_fmaddn_inplace(d->m_ctx, a, b.data(), c, csize), "fmaddn_inplace");
+}
+
+void nbody_engine_b200::fmaddn_corr(memory* _a, memory* _corr, const memory_array& _b, const nbcoord_t* c, size_t csize)
+{
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	corr = d->handle(_corr, "corr");
+	if(corr == nullptr)
+	{
+		return;
+	}
+	if(c == nullptr)
+	{
+		qDebug() << "c must not be nullptr";
+		return;
+	}
+	if(csize > _b.size())
+	{
+		qDebug() << "csize > b.size()";
+		return;
+	}
+	std::vector<const nb200_buf*>	b(handles(_b, csize, d->m_ctx));
+	d->check(nb200_fmaddn_corr(d->m_ctx, a, corr, b.data(), c, csize), "fmaddn_corr");
+}
+
+void nbody_engine_b200::fmaddn(memory* _a, const memory* _b, const memory_array& _c, const nbcoord_t* _d, size_t dsize)
+{
+	if(_d == NULL)
+	{
+		qDebug() << "d == NUL";
+		return;
+	}
+	if(dsize > _c.size())
+	{
+		qDebug() << "dsize > c.size()";
+		return;
+	}
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	nb200_buf*	b = nullptr;
+	if(_b != NULL)
+	{
+		b = d->handle(_b, "b");
+		if(b == nullptr)
+		{
+			return;
+		}
+	}
+	std::vector<const nb200_buf*>	c(handles(_c, dsize, d->m_ctx));
+	d->check(nb200_fmaddn(d->m_ctx, a, b, c.data(), _d, dsize), "fmaddn");
+}
+
+void nbody_engine_b200::fmaxabs(const memory* _a, nbcoord_t& result)
+{
+	nb200_buf*	a = d->handle(_a, "a");
+	if(a == nullptr)
+	{
+		return;
+	}
+	nb200_real	r = 0;
+	if(nb200_fmaxabs(d->m_ctx, a, &r) == NB200_OK)
+	{
+		result = r;
+	}
+	else
+	{
+		qDebug() << "fmaxabs" << nb200_last_error(d->m_ctx);
+	}
+}
+
+void nbody_engine_b200::print_info() const
+{
+	qDebug() << "\tSelected B200 devices:";
+	if(d->m_ctx != nullptr)
+	{
+		char	text[4096];
+		if(nb200_describe(d->m_ctx, text, sizeof(text)) == NB200_OK)
+		{
+			qDebug() << text;
+		}
+	}
+	else
+	{
+		for(size_t n = 0; n != d->m_device_ids.size(); ++n)
+		{
+			qDebug() << "\t #" << n << "ID" << d->m_device_ids[n];
+		}
+	}
+	if(d->m_force == ef_barnes_hut)
+	{
+		qDebug() << "\t" << "distance_to_node_radius_ratio:" << d->m_ratio;
+		qDebug() << "\t" << "traverse_type:" << "nested_tree";
+		qDebug() << "\t" << "tree_layout:" << tree_layout_name(d->m_tree_layout);
+		qDebug() << "\t" << "tree_build_rate:" << d->m_tree_build_rate;
+	}
+}
+
+int nbody_engine_b200::select_devices(const QString& devices_str)
+{
+	QStringList	dev_list(devices_str.split(",", QString::SkipEmptyParts));
+	if(dev_list.isEmpty())
+	{
+		qDebug() << "CUDA device list is empty";
+		return -1;
+	}
+	int	device_count = 0;
+	if(nb200_device_count(&device_count) != NB200_OK || device_count <= 0)
+	{
+		qDebug() << "No CUDA devices found";
+		return -1;
+	}
+	std::vector<int>	device_ids;
+	for(int i = 0; i != dev_list.size(); ++i)
+	{
+		bool	ok = false;
+		int		dev_id = dev_list[i].toInt(&ok);
+		if(!ok)
+		{
+			qDebug() << "Can't parse device ID" << dev_list[i];
+			return -1;
+		}
+		if(dev_id < 0 || dev_id >= device_count)
+		{
+			qDebug() << "Invalid device ID" << dev_id << "must be in range [0 ..." << device_count << ")";
+			return -1;
+		}
+		device_ids.push_back(dev_id);
+	}
+	d->m_device_ids = device_ids;
+	return 0;
+}
+
+void nbody_engine_b200::set_block_size(int block_size)
+{
+	Q_UNUSED(block_size);
+}
+
+void nbody_engine_b200::set_use_nccl(bool active)
+{
+	Q_UNUSED(active);
+}
+
+nbody_engine* nbody_create_engine_b200(const QVariantMap& param)
+{
+	const QString type(param.value("engine").toString());
+	nbody_engine_b200*	engine = nullptr;
+	if(type == "b200")
+	{
+		engine = new nbody_engine_b200();
+	}
+	else if(type == "b200_bh")
+	{
+		nbcoord_t	ratio = param.value("distance_to_node_radius_ratio", 10).toDouble();
+		size_t		tree_build_rate = param.value("tree_build_rate", 0).toULongLong();
+		QString		strtl(param.value("tree_layout", "heap_stackless").toString());
+		e_tree_layout tl = tree_layout_from_str(strtl);
+		if(tl != etl_heap && tl != etl_heap_stackless)
+		{
+			qDebug() << "Invalid tree_layout. Allowed values are 'heap' or 'heap_stackless'";
+			return NULL;
+		}
+		engine = new nbody_engine_b200(nbody_engine_b200::ef_barnes_hut, ratio, tree_build_rate, tl);
+	}
+	else
+	{
+		return NULL;
+	}
+	QString	devices(param.value("device", "0").toString());
+	if(0 != engine->select_devices(devices))
+	{
+		delete engine;
+		return NULL;
+	}
+	engine->set_block_size(param.value("block_size", NBODY_DATA_BLOCK_SIZE).toInt());
+	engine->set_use_nccl(param.value("use_nccl", false).toBool());
+	return engine;
+}
+
+// Plain-C doorway for the ctypes test harness: "engine=b200_bh;device=0,0;tree_layout=heap"
+extern "C" __attribute__((visibility("default"))) void* nbody_engine_b200_create(const char* params)
+{
+	QVariantMap	m;
+	QStringList	items(QString(params ? params : "").split(";", QString::SkipEmptyParts));
+	for(int i = 0; i < items.size(); ++i)
+	{
+		int eq = items[i].indexOf("=");
+		if(eq >= 0)
+		{
+			m[items[i].mid(0, eq).trimmed()] = QVariant(items[i].mid(eq + 1).trimmed());
+		}
+	}
+	return nbody_create_engine_b200(m);
+}

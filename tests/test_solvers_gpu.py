@@ -1,0 +1,159 @@
+"""Every reference solver drives the B200 engine unchanged: the reference's own solver classes (compiled
+unmodified into oracle/_ref) run on nbody_engine_b200 (the C++ adapter over the C ABI) and must reproduce
+the reference's golden end states -- test/solver/test_nbody_solver.cpp, tolerance 1e-12 absolute."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_path, load_golden_npz
+
+pytestmark = pytest.mark.gpu
+
+BUTCHER = dict(max_recursion=1, substep_subdivisions=2, refine_steps_count=1, error_threshold=1e-5)
+CASES = [
+    ("adams5", dict(solver="adams", rank=5)),
+    ("adams5-corr", dict(solver="adams", rank=5, correction="true")),
+    ("bulirsch-stoer", dict(solver="bs", max_level=4, min_step=1e-5)),
+    ("euler", dict(solver="euler")),
+    ("midpoint", dict(solver="midpoint")),
+    ("midpoint-st", dict(solver="midpoint-st")),
+    ("rk4", dict(solver="rk4")),
+    ("rkck", dict(solver="rkck", **BUTCHER)),
+    ("rkdp", dict(solver="rkdp", correction="false", **BUTCHER)),
+    ("rkdp-corr", dict(solver="rkdp", correction="true", **BUTCHER)),
+    ("rkdverk", dict(solver="rkdverk", **BUTCHER)),
+    ("rkf", dict(solver="rkf", **BUTCHER)),
+    ("rkfeagin10", dict(solver="rkfeagin10", **BUTCHER)),
+    ("rkfeagin10-corr", dict(solver="rkfeagin10", correction="true", **BUTCHER)),
+    ("rkfeagin12", dict(solver="rkfeagin12", **BUTCHER)),
+    ("rkfeagin14", dict(solver="rkfeagin14", **BUTCHER)),
+    ("rkgl", dict(solver="rkgl", **BUTCHER)),
+    ("rklc", dict(solver="rklc", **BUTCHER)),
+    ("trapeze2", dict(solver="trapeze", refine_steps_count=2)),
+]
+
+
+@pytest.fixture(scope="module")
+def adapter(ref64):
+    from nbody_b200 import build
+    path = build.adapter_path("f64")
+    if not os.path.exists(path):
+        pytest.skip("C++ adapter not built (needs the reference headers at build time)")
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+    lib.nbody_engine_b200_create.restype = C.c_void_p
+    lib.nbody_engine_b200_create.argtypes = [C.c_char_p]
+    return lib
+
+
+def b200_engine(ref64, adapter, **kw):
+    from oracle import refharness as R
+    h = adapter.nbody_engine_b200_create(R.params(**kw))
+    assert h, "factory returned NULL for %r" % (kw,)
+    return R.Engine(ref64, handle=h)
+
+
+def run_golden(ref64, engine, name, params):
+    from oracle import refharness as R
+    d = R.Data(ref64).load(golden_path("initial_state.txt"))
+    assert engine.init(d)
+    s = R.Solver(ref64, **params)
+    s.set_time_step(1e-3, 3e-2)
+    s.set_engine(engine)
+    assert s.run(d, 0.3) == 0
+    engine.get_data(d)
+    expected = R.Data(ref64).load(golden_path(name + ".txt"))
+    y, _ = d.export()
+    ye, _ = expected.export()
+    ok = d.is_equal(expected, 1e-12)
+    s.close()          # before the engine: solver destructors free their buffers through engine()
+    engine.close()
+    return ok, float(np.abs(y - ye).max())
+
+
+@pytest.mark.parametrize("name,params", CASES, ids=[c[0] for c in CASES])
+def test_reference_solver_golden_on_b200(ref64, adapter, name, params):
+    ok, err = run_golden(ref64, b200_engine(ref64, adapter, engine="b200"), name, params)
+    assert ok, "max |dy| = %g" % err
+
+
+@pytest.mark.parametrize("kw", [dict(engine="b200", device="0,0"),
+                                dict(engine="b200_bh", distance_to_node_radius_ratio=1e8),
+                                dict(engine="b200_bh", distance_to_node_radius_ratio=1e8, device="0,0", tree_layout="heap")],
+                         ids=["b200-2lanes", "b200_bh-1e8", "b200_bh-1e8-heap-2lanes"])
+def test_euler_golden_on_engine_variants(ref64, adapter, kw):
+    """The reference re-runs the euler golden on opencl / opencl_bh(1e8) and multi-device lists
+    (test_nbody_solver.cpp:267-297); same here for the b200 aliases."""
+    ok, err = run_golden(ref64, b200_engine(ref64, adapter, **kw), "euler", dict(solver="euler"))
+    assert ok, "max |dy| = %g" % err
+
+
+def test_factory_rejects_bad_parameters(ref64, adapter):
+    from oracle import refharness as R
+    for bad in ("", "a", "0,a", "-1", "9999"):
+        assert not adapter.nbody_engine_b200_create(R.params(engine="b200", device=bad))
+    assert not adapter.nbody_engine_b200_create(R.params(engine="b200_bh", tree_layout="tree"))
+    assert not adapter.nbody_engine_b200_create(R.params(engine="cuda"))
+
+
+def test_adapter_fcompute_vs_simple_engine(ref64, adapter):
+    """test_fcompute(e0 = nbody_engine_simple, e1) of test_nbody_engine.cpp:472-558 with the reference's
+    default eps 1e-13, N = 128 and 256, two steps with y *= 0.99... (fmadd_inplace(y, y, -0.01) here)."""
+    from oracle import refharness as R
+    for stars in (64, 128):
+        d = R.Data(ref64).make_universe(stars)
+        e0 = R.Engine(ref64, engine="simple")
+        e1 = b200_engine(ref64, adapter, engine="b200")
+        assert e0.init(d) and e1.init(d)
+        y0, y1 = e0.create_buffer(e0.size(e0.get_y())), e1.create_buffer(e1.size(e1.get_y()))
+        e0.copy_buffer(y0, e0.get_y())
+        e1.copy_buffer(y1, e1.get_y())
+        nbytes = e0.problem_size() * 8
+        for step in range(2):
+            f0, f1 = e0.create_buffer(nbytes), e1.create_buffer(nbytes)
+            e0.fill_buffer(f0, 1e10)
+            e1.fill_buffer(f1, -1e10)
+            e0.fcompute(0, y0, f0)
+            e1.fcompute(0, y1, f1)
+            a, b = e0.read_buffer(f0), e1.read_buffer(f1)
+            assert np.abs(a - b).max() <= 1e-13
+            e0.free_buffer(f0)
+            e1.free_buffer(f1)
+            e0.fmadd_inplace(y0, y0, -0.01)
+            e1.fmadd_inplace(y1, y1, -0.01)
+        assert e1.compute_count() == 2
+        for e, y in ((e0, y0), (e1, y1)):
+            e.free_buffer(y)
+            e.close()
+        d.close()
+
+
+def test_c1_rk4_drift_matches_openmp_engine(ref64, adapter):
+    """BASELINE config C1 (--engine=openmp --solver=rk4 --stars_count=1024, G1): the conservation report of
+    nbody_data::print_statistics (dP, dL, dE, centre-of-mass drift) after 10 rk4 steps agrees between the
+    reference's openmp engine and the b200 engine."""
+    from oracle import refharness as R
+    stats = {}
+    for name, make in (("openmp", lambda: R.Engine(ref64, engine="openmp")),
+                       ("b200", lambda: b200_engine(ref64, adapter, engine="b200"))):
+        d = R.Data(ref64).make_universe(1024)
+        e = make()
+        assert e.init(d)
+        s = R.Solver(ref64, solver="rk4", max_step=1e-2, min_step=1e-9)
+        s.set_engine(e)
+        first = d.statistics(e, "PLVE")
+        assert s.run(d, 0.1) == 0
+        last = d.statistics(e, "PLVE")
+        y, _ = d.export()
+        stats[name] = (first, last, y, e.compute_count())
+        s.close()
+        e.close()
+        d.close()
+    a, b = stats["openmp"], stats["b200"]
+    assert a[3] == b[3] == 40                                # 10 steps x 4 fcompute: CC column of the report
+    assert np.abs(a[2] - b[2]).max() <= 1e-10               # trajectories agree
+    for key in ("E", "P", "L"):
+        assert b[1][key] == pytest.approx(a[1][key], rel=1e-11)
+    for key in ("dP", "dL", "dE"):
+        assert abs(a[1][key] - b[1][key]) <= 1e-9            # per cent of the initial value
