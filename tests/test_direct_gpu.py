@@ -136,3 +136,19 @@ def test_direct_c3_n1m_sampled_and_momentum(oracle64):
     force = (f[3:] * m[None, :]).sum(axis=1)
     scale = np.abs(f[3:] * m[None, :]).sum(axis=1)
     assert np.all(np.abs(force) <= 1e-10 * scale)
+
+
+def test_multi_process_nccl_two_ranks():
+    """One process per GPU over NCCL (skipped on a single-GPU box; the gloo tests cover the host logic there)."""
+    import os
+    import subprocess
+    import sys
+    from nbody_b200 import device_count
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "mp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "mp_check direct ok" in out.stdout and "mp_check bh ok" in out.stdout
