@@ -1064,6 +1064,7 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
 	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_block = value; }	// 0 = warp-coherent, 1 = one thread per target
+	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
 	else if(strcmp(name, "timing") == 0) { ctx->opt_timing = value; }
 	else { return fail(ctx, NB200_ERR_ARG, "set_option: unknown option %s", name); }
 	return NB200_OK;

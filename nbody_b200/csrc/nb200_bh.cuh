@@ -351,7 +351,7 @@ __device__ __forceinline__ void store_f(const real* __restrict__ y, real* __rest
 }
 
 // one thread per target, independent stackless walks (the reference kernel's shape)
-__global__ void __launch_bounds__(128) bh_walk_thread(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+__global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 													   const int* __restrict__ body_n, const int* __restrict__ own_leaf,
 													   const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													   size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
@@ -389,8 +389,13 @@ __global__ void __launch_bounds__(128) bh_walk_thread(const node4* __restrict__ 
 	}
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // one warp per 32 consecutive targets, warp-uniform walk over the union of the lanes' traversals
-__global__ void __launch_bounds__(128) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+__global__ void __launch_bounds__(256) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 													 const int* __restrict__ body_n, const int* __restrict__ own_leaf,
 													 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
@@ -399,7 +404,6 @@ __global__ void __launch_bounds__(128) bh_walk_warp(const node4* __restrict__ xy
 	const bool	live = t < n_targets;
 	const int	tc = live ? t : n_targets - 1;	// idle lanes shadow the last target and never store
 	const int	leaf = n + (own_leaf != nullptr ? own_leaf[tc] : tc);
-	const int	tree_size = 2 * n;
 	const node4	me = load_node(xyzr, leaf);
 	real		ax = 0, ay = 0, az = 0;
 	unsigned	visits = 0, inter = 0;
@@ -409,12 +413,22 @@ __global__ void __launch_bounds__(128) bh_walk_warp(const node4* __restrict__ xy
 	do
 	{
 		const node4	nd = load_node(xyzr, curr);	// same address in every lane: one broadcast transaction
+		const int	skip = heap_skip_idx(curr);	// one BREV + FLO per visit, shared by the sleeping rule and the step
+		const int	child = curr << 1;
+#ifdef NB200_BH_PREFETCH
+		if(child < 2 * n)
+		{
+			// both children share one 64-byte block (measured: no gain on B200 -- the walk is issue-bound, not latency-bound)
+			prefetch_l1(xyzr + child);
+		}
+#endif
 		awake = awake || (curr == resume);
 		real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
 		real d2 = dx * dx + dy * dy + dz * dz;
-		const bool accept = awake && (d2 > nd.w);
-		const bool open = awake && !accept;
-		if(awake) { ++visits; }
+		const bool far = d2 > nd.w;
+		const bool accept = awake && far;
+		const bool open = awake && !far;
+		visits += awake ? 1u : 0u;
 		if(__any_sync(0xffffffffu, accept))
 		{
 			const real m = nmass[curr];
@@ -423,11 +437,11 @@ __global__ void __launch_bounds__(128) bh_walk_warp(const node4* __restrict__ xy
 				node_force(me.x, me.y, me.z, nd, m, ax, ay, az);
 				++inter;
 				awake = false;
-				resume = heap_skip_idx(curr);
+				resume = skip;
 			}
 		}
-		// descend if any awake lane needs the children (leaves have none: heap_next_up falls back to skip_idx)
-		curr = __any_sync(0xffffffffu, open) ? heap_next_up(curr, tree_size) : heap_skip_idx(curr);
+		// descend if any awake lane needs the children; leaves have none (heap_next_up falls back to skip_idx)
+		curr = (__any_sync(0xffffffffu, open) && child < 2 * n) ? child : skip;
 	} while(curr != 1);
 	if(live)
 	{
@@ -615,7 +629,7 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	const int	n_targets = static_cast<int>(ctx->n_shard);
 	const int*	own = ctx->nshards > 1 ? s->own_leaf : nullptr;
 	const int	shard_first = static_cast<int>(static_cast<size_t>(l.shard) * ctx->n_shard);
-	const int	block = 128;
+	const int	block = (ctx->opt_walk_threads == 64 || ctx->opt_walk_threads == 256) ? static_cast<int>(ctx->opt_walk_threads) : 128;
 	const unsigned grid = static_cast<unsigned>((n_targets + block - 1) / block);
 	if(ctx->opt_walk_block == 1)
 	{
