@@ -38,8 +38,9 @@ os.environ.setdefault("NBREF_QUIET", "1")
 N_DIRECT = 1 << 20
 N_BH = 1 << 22
 N_CPU_SAMPLE = 32768
-SLOTS_PER_PAIR = 18          # FP64-pipe instruction slots per pair (the kernel issues 17)
-FLOP_PER_PAIR = 2 * SLOTS_PER_PAIR
+# FMA-pipe instruction slots per pair -- FP64: 18 (the kernel issues 17); FP32: 13 (+1 MUFU on XU)
+SLOTS_PER_PAIR = {"f64": 18, "f32": 13}
+ISSUED_PER_PAIR = {"f64": 17, "f32": 13}
 
 
 def parse_args():
@@ -221,12 +222,12 @@ def run_nb200(args):
     import torch  # noqa: F401  (device selection / pinned memory / rendezvous only)
     from nbody_b200 import Engine, dist, new_unique_id
 
+    _, world_env, local_env = dist.env_rank()
+    if world_env > 1:
+        torch.cuda.set_device(local_env)          # before the NCCL process group touches a device
     rank, world, local = dist.init_process_group()
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE is %d: launch with torch.distributed.run" % (args.gpus, world))
-    if world > 1:
-        import torch as _t
-        _t.cuda.set_device(local)
     direct = args.workload == "direct"
     n = args.bodies or (N_DIRECT if direct else N_BH)
     precision = args.precision
@@ -315,15 +316,17 @@ def run_nb200(args):
             metric = "pair interactions/s (%s direct all-pairs fcompute, N=%d)" % ("FP64" if precision == "f64" else "FP32", n)
             # dominant kernel: direct_pairs; each rank's launch covers n/world targets x n sources
             pairs_per_launch = pairs / world
-            achieved = pairs_per_launch * FLOP_PER_PAIR / (force_ms * 1e-3) / 1e12
+            slots, issued = SLOTS_PER_PAIR[precision], ISSUED_PER_PAIR[precision]
+            achieved = pairs_per_launch * 2 * slots / (force_ms * 1e-3) / 1e12
             peak = fma_peak * 2 / 1e12
             roofline = {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe",
                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                        "traffic": None, "kernel": "direct_pairs<4>", "kernel_ms": force_ms,
-                        "algorithmic_per_unit": "%d FP64-pipe slots = %d flop per pair (SURVEY 8d); kernel issues 17" % (SLOTS_PER_PAIR, FLOP_PER_PAIR),
-                        "frac_issued_17": (pairs_per_launch * 17 / (force_ms * 1e-3)) / fma_peak if fma_peak else None,
-                        "peak_source": "nb200_probe_fma_peak (DFMA chain kernel, this run); MEASURED_PEAKS.json has no FP64 entry; "
-                                       "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s"}
+                        "traffic": None, "kernel": "direct_pairs", "kernel_ms": force_ms,
+                        "algorithmic_per_unit": "%d FMA-pipe slots = %d flop per pair (SURVEY 8d); kernel issues %d" % (slots, 2 * slots, issued),
+                        "frac_issued": (pairs_per_launch * issued / (force_ms * 1e-3)) / fma_peak if fma_peak else None,
+                        "peak_source": "nb200_probe_fma_peak (FMA chain kernel of this precision, this run); MEASURED_PEAKS.json has no "
+                                       "FP64/FP32 vector entry; nominal 148 SM x 64 (FP64) / 128 (FP32) FMA/clk x 1.965 GHz = 37.2 / 74.4 TFLOP/s",
+                        "traffic_note": "ncu --set full (profiles/r1_ncu_direct_pairs.csv): 48 MB DRAM read + 60 MB written per launch at N=1M"}
             e2e_obj = None
             if e2e:
                 e2e_obj = {"value": pairs * args.steps / e2e[0], "unit": unit, "h2d_bytes_per_step": e2e[1],

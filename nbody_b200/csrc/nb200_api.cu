@@ -650,14 +650,16 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	const int	n_tiles = static_cast<int>(ctx->n_pad / NB200_DIRECT_TILE);
 	const int	sms = ctx->lanes[0].sm_count;
 	// Targets per thread: as many as still leave >= 2 CTAs per SM worth of (target block, tile) items.
+	// FP32 pairs are issue-bound (13 FFMA-pipe + MUFU + FMNMX per pair): 8 targets per thread halve the LDS share.
+	const int	ipt_max = sizeof(real) == 4 ? 8 : 4;
 	int ipt = 1;
-	if(ctx->opt_direct_ipt == 1 || ctx->opt_direct_ipt == 2 || ctx->opt_direct_ipt == 4)
+	if(ctx->opt_direct_ipt == 1 || ctx->opt_direct_ipt == 2 || ctx->opt_direct_ipt == 4 || (ctx->opt_direct_ipt == 8 && ipt_max == 8))
 	{
 		ipt = static_cast<int>(ctx->opt_direct_ipt);
 	}
 	else
 	{
-		for(int cand = 4; cand >= 1; cand >>= 1)
+		for(int cand = ipt_max; cand >= 1; cand >>= 1)
 		{
 			size_t blocks = (ctx->n_shard + NB200_DIRECT_THREADS * cand - 1) / (NB200_DIRECT_THREADS * cand);
 			if(blocks * static_cast<size_t>(n_tiles) >= static_cast<size_t>(2 * sms) || cand == 1)
@@ -701,6 +703,9 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 		const int write_f = segments == 1 ? 1 : 0;
 		switch(ipt)
 		{
+#if NB200_PRECISION == 1
+		case 8: launch_pairs<8>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;
+#endif
 		case 4: launch_pairs<4>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;
 		case 2: launch_pairs<2>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;
 		default: launch_pairs<1>(ctx, l, lane_ptr(y, li), out, grid, n_tiles, tiles_per_seg, write_f); break;

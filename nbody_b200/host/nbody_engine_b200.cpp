@@ -528,6 +528,19 @@ void nbody_engine_b200::set_use_nccl(bool active)
 	Q_UNUSED(active);
 }
 
+unsigned long long nbody_engine_b200::launch_count() const
+{
+	return nb200_launch_count(d->m_ctx);
+}
+
+void nbody_engine_b200::synchronize()
+{
+	if(d->m_ctx != nullptr)
+	{
+		nb200_sync(d->m_ctx);
+	}
+}
+
 nbody_engine* nbody_create_engine_b200(const QVariantMap& param)
 {
 	const QString type(param.value("engine").toString());
@@ -578,4 +591,19 @@ extern "C" __attribute__((visibility("default"))) void* nbody_engine_b200_create
 		}
 	}
 	return nbody_create_engine_b200(m);
+}
+
+extern "C" __attribute__((visibility("default"))) unsigned long long nbody_engine_b200_launch_count(void* engine)
+{
+	nbody_engine_b200* e = dynamic_cast<nbody_engine_b200*>(static_cast<nbody_engine*>(engine));
+	return e != nullptr ? e->launch_count() : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) void nbody_engine_b200_synchronize(void* engine)
+{
+	nbody_engine_b200* e = dynamic_cast<nbody_engine_b200*>(static_cast<nbody_engine*>(engine));
+	if(e != nullptr)
+	{
+		e->synchronize();
+	}
 }

@@ -66,6 +66,10 @@ public:
 	void set_block_size(int block_size);
 	//! Single-process lanes exchange shards by peer copies; NCCL is used by the one-process-per-GPU mode only
 	void set_use_nccl(bool);
+	//! Kernels launched so far (instrumentation)
+	unsigned long long launch_count() const;
+	//! Block until all queued device work has finished
+	void synchronize();
 private:
 	bool ensure_context();
 	struct	data;
