@@ -355,6 +355,26 @@ def run_nb200(args):
                 e2e_obj = {"value": e2e[0] * 1e3 / args.steps, "unit": unit, "h2d_bytes_per_step": e2e[1],
                            "d2h_bytes_per_step": e2e[2], "result_maxabs": e2e[3]}
             hib = False
+        # context row: the reference's own CUDA kernel recompiled for sm_100a, same box, same inputs (N bounded for direct)
+        ref_cuda = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import refcuda
+                if refcuda.available(precision):
+                    if direct:
+                        nr = min(n, 262144)
+                        yr, mr, _ = (y, m, None) if nr == n else make_inputs(nr, precision)
+                        _, ms_ref = refcuda.direct(yr, mr, block_size=256, reps=1, precision=precision)
+                        ref_cuda = {"kernel": "kfcompute + kfcompute_xyz (nbody_engine_cuda_impl.cu:10-124) recompiled for sm_100a, block 256",
+                                    "bodies": nr, "value": float(nr) * nr / (ms_ref * 1e-3), "unit": unit, "ms": ms_ref}
+                    else:
+                        tree = eng.bh_export_tree()
+                        _, ms_ref = refcuda.bh_stackless(y, tree[0], tree[1], tree[2], block_size=256, reps=1, precision=precision)
+                        ref_cuda = {"kernel": "kfcompute_heap_bh_stackless (nbody_engine_cuda_impl.cu:372-451) recompiled for sm_100a, block 256, "
+                                              "walk only on nb200's tree (the reference adds a CPU tree build + transfers per step)",
+                                    "bodies": n, "value": ms_ref, "unit": "ms (walk only)"}
+            except Exception as exc:
+                ref_cuda = {"error": repr(exc)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -371,7 +391,7 @@ def run_nb200(args):
                        "l2": "256 MiB fill kernel between timed iterations (L2 flush, inside the timed region)",
                        "phases_ms_last_step": phases},
             "clocks": clocks, "e2e": e2e_obj, "gpu_launches": int(launches) * world,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_cuda_kernel": ref_cuda,
         }
         print(json.dumps(line))
     eng.free_buffer(fbuf)
