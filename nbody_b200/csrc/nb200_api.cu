@@ -15,6 +15,7 @@
 #include "nb200_common.cuh"
 #include "nb200_comm.cuh"
 #include "nb200_direct.cuh"
+#include "nb200_direct_sym.cuh"
 #include "nb200_stateops.cuh"
 #include "nb200_bh.cuh"
 
@@ -91,6 +92,15 @@ void free_lane(nb200_lane& l)
 	if(l.mass) { cudaFree(l.mass); }
 	if(l.src) { cudaFree(l.src); }
 	if(l.partial) { cudaFree(l.partial); }
+	if(l.sym_tiles) { cudaFree(l.sym_tiles); }
+	if(l.sym_prow) { cudaFree(l.sym_prow); }
+	if(l.sym_pcol) { cudaFree(l.sym_pcol); }
+	if(l.sym_acc) { cudaFree(l.sym_acc); }
+	l.sym_tiles = nullptr;
+	l.sym_prow = l.sym_pcol = l.sym_acc = nullptr;
+	l.sym_ntiles = 0;
+	l.sym_edge = 0;
+	l.partial_elems = 0;
 	if(l.d_scalar) { cudaFree(l.d_scalar); }
 	if(l.h_scalar) { cudaFreeHost(l.h_scalar); }
 	l.mass = nullptr;
@@ -433,20 +443,27 @@ NB200_API int nb200_set_bodies(nb200_ctx* ctx, size_t n, const nb200_real* mass)
 	ctx->n = n;
 	ctx->n_shard = n / static_cast<size_t>(ctx->nshards);
 	ctx->n_pad = (n + NB200_DIRECT_TILE - 1) / NB200_DIRECT_TILE * NB200_DIRECT_TILE;
+	ctx->n_alloc = (n + 8191) / 8192 * 8192;	// room for the zero-mass padding of the largest symmetric tile edge
 	for(auto& l : ctx->lanes)
 	{
 		CU(ctx, cudaSetDevice(l.dev));
 		if(l.mass) { cudaFree(l.mass); l.mass = nullptr; }
 		if(l.src) { cudaFree(l.src); l.src = nullptr; }
+		if(l.sym_tiles) { cudaFree(l.sym_tiles); l.sym_tiles = nullptr; }
+		if(l.sym_prow) { cudaFree(l.sym_prow); l.sym_prow = nullptr; }
+		if(l.sym_pcol) { cudaFree(l.sym_pcol); l.sym_pcol = nullptr; }
+		if(l.sym_acc) { cudaFree(l.sym_acc); l.sym_acc = nullptr; }
+		l.sym_edge = 0;
+		l.sym_ntiles = 0;
 		bh_free(l.bh);
 		l.bh = nullptr;
-		if(cudaMalloc(&l.mass, n * sizeof(real)) != cudaSuccess || cudaMalloc(&l.src, ctx->n_pad * sizeof(body4)) != cudaSuccess)
+		if(cudaMalloc(&l.mass, n * sizeof(real)) != cudaSuccess || cudaMalloc(&l.src, ctx->n_alloc * sizeof(body4)) != cudaSuccess)
 		{
 			cudaGetLastError();
 			return fail(ctx, NB200_ERR_ALLOC, "set_bodies: device allocation failed");
 		}
 		// Padding bodies have zero mass: they contribute exactly 0 to every sum.
-		CU(ctx, cudaMemsetAsync(l.src, 0, ctx->n_pad * sizeof(body4), l.stream));
+		CU(ctx, cudaMemsetAsync(l.src, 0, ctx->n_alloc * sizeof(body4), l.stream));
 		CU(ctx, cudaMemcpyAsync(l.mass, mass, n * sizeof(real), cudaMemcpyHostToDevice, l.stream));
 		CU(ctx, cudaStreamSynchronize(l.stream));
 	}
@@ -639,6 +656,111 @@ NB200_API int nb200_fill(nb200_ctx* ctx, nb200_buf* a, nb200_real value)
 }
 
 // ---- direct all-pairs --------------------------------------------------------------
+namespace {
+#if NB200_PRECISION == 2
+// Tile edge of the symmetric path for this problem, 0 = use the plain kernel.
+int sym_tile_edge(const nb200_ctx* ctx)
+{
+	if(ctx->lanes.size() != 1 || ctx->opt_direct_sym == 0) { return 0; }
+	if(ctx->opt_direct_sym < 0 && ctx->n < 196608) { return 0; }	// too few tiles to fill 148 SMs
+	long long edge = ctx->opt_sym_tile > 0 ? ctx->opt_sym_tile : (ctx->n >= 786432 ? 8192 : 4096);
+	// 8 column blocks per phase round, 32*J bodies each; 32*I bodies per row block
+	const long long unit = ctx->opt_sym_shape == 3 ? 1024 : (ctx->opt_sym_shape >= 1 ? 512 : 256);
+	if(edge % unit != 0 || edge % 256 != 0 || edge > 8192) { return 0; }
+	return static_cast<int>(edge);
+}
+
+int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
+{
+	nb200_lane&		l = ctx->lanes[0];
+	const int		S = static_cast<int>((ctx->n + T - 1) / T);
+	const long long	total = static_cast<long long>(S) * (S + 1) / 2;
+	const size_t	mine = static_cast<size_t>((total - ctx->rank + ctx->nranks - 1) / ctx->nranks);
+	CU(ctx, cudaSetDevice(l.dev));
+	if(l.sym_edge != T || l.sym_ntiles != mine)
+	{
+		if(l.sym_tiles) { cudaFree(l.sym_tiles); }
+		if(l.sym_prow) { cudaFree(l.sym_prow); }
+		if(l.sym_pcol) { cudaFree(l.sym_pcol); }
+		if(l.sym_acc) { cudaFree(l.sym_acc); }
+		l.sym_tiles = nullptr;
+		l.sym_prow = l.sym_pcol = l.sym_acc = nullptr;
+		l.sym_edge = 0;
+		std::vector<int2> rc;
+		rc.reserve(mine);
+		long long id = 0;
+		for(int r = 0; r < S; ++r)
+		{
+			for(int c = r; c < S; ++c, ++id)
+			{
+				if(id % ctx->nranks == ctx->rank) { rc.push_back(make_int2(r, c)); }
+			}
+		}
+		const size_t tile_bytes = 3 * static_cast<size_t>(T) * sizeof(real);
+		if(cudaMalloc(&l.sym_tiles, std::max<size_t>(1, mine) * sizeof(int2)) != cudaSuccess ||
+		   cudaMalloc(&l.sym_prow, std::max<size_t>(1, mine) * tile_bytes) != cudaSuccess ||
+		   cudaMalloc(&l.sym_pcol, std::max<size_t>(1, mine) * tile_bytes) != cudaSuccess ||
+		   cudaMalloc(&l.sym_acc, (3 * ctx->n + 3 * ctx->n_shard) * sizeof(real)) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return fail(ctx, NB200_ERR_ALLOC, "fcompute_direct: symmetric-tile scratch allocation failed (%zu tiles of %d)", mine, T);
+		}
+		CU(ctx, cudaMemcpyAsync(l.sym_tiles, rc.data(), mine * sizeof(int2), cudaMemcpyHostToDevice, l.stream));
+		CU(ctx, cudaStreamSynchronize(l.stream));
+		l.sym_edge = T;
+		l.sym_ntiles = mine;
+	}
+	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[2], l.stream)); }
+	const size_t smem = 3 * static_cast<size_t>(T) * sizeof(real);
+	if(mine > 0)
+	{
+		if(ctx->opt_sym_shape == 2)
+		{
+			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			direct_sym_tiles<8, 2><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
+				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		}
+		else if(ctx->opt_sym_shape == 3)
+		{
+			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			direct_sym_tiles<4, 4><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
+				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		}
+		else if(ctx->opt_sym_shape == 1)
+		{
+			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			direct_sym_tiles<4, 2><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
+				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		}
+		else
+		{
+			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			direct_sym_tiles<8, 1><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
+				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		}
+		LAUNCHED(ctx);
+	}
+	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[3], l.stream)); }
+	direct_sym_reduce<<<static_cast<unsigned>((ctx->n + 255) / 256), 256, 0, l.stream>>>(
+		l.sym_prow, l.sym_pcol, l.sym_acc, ctx->n, ctx->n_shard, T, S, ctx->rank, ctx->nranks);
+	LAUNCHED(ctx);
+	const real* acc = l.sym_acc;
+	if(ctx->nranks > 1)
+	{
+		real* mine_acc = l.sym_acc + 3 * ctx->n;
+		NC(ctx, ctx->nccl->ReduceScatter(l.sym_acc, mine_acc, 3 * ctx->n_shard, NB200_NCCL_REAL, ncclSum,
+										 static_cast<ncclComm_t>(ctx->comm), l.stream));
+		acc = mine_acc;
+	}
+	direct_sym_finish<<<static_cast<unsigned>((3 * ctx->n_shard + 255) / 256), 256, 0, l.stream>>>(
+		acc, lane_ptr(y, 0), lane_ptr(f, 0), ctx->n_shard);
+	LAUNCHED(ctx);
+	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }
+	return NB200_OK;
+}
+#endif
+}  // namespace
+
 NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f)
 {
 	int rc = check_state_pair(ctx, y, f, "fcompute_direct");
@@ -646,6 +768,12 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_direct: y and f must differ"); }
 	rc = pack_and_gather(ctx, y);
 	if(rc != NB200_OK) { return rc; }
+#if NB200_PRECISION == 2
+	if(const int edge = sym_tile_edge(ctx))
+	{
+		return sym_fcompute(ctx, y, f, edge);
+	}
+#endif
 
 	const int	n_tiles = static_cast<int>(ctx->n_pad / NB200_DIRECT_TILE);
 	const int	sms = ctx->lanes[0].sm_count;
@@ -1070,6 +1198,9 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
 	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_block = value; }	// 0 = warp-coherent, 1 = one thread per target
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
+	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; }	// -1 auto, 0 off, 1 on
+	else if(strcmp(name, "direct_sym_tile") == 0) { ctx->opt_sym_tile = value; }
+	else if(strcmp(name, "direct_sym_shape") == 0) { ctx->opt_sym_shape = value; }
 	else if(strcmp(name, "timing") == 0) { ctx->opt_timing = value; }
 	else { return fail(ctx, NB200_ERR_ARG, "set_option: unknown option %s", name); }
 	return NB200_OK;

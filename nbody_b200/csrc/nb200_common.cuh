@@ -53,6 +53,13 @@ struct nb200_lane
 	body4*			src = nullptr;      // packed sources for all N bodies (+ zero-mass padding)
 	real*			partial = nullptr;  // [S][3][n_shard] partial accelerations (direct, S>1)
 	size_t			partial_elems = 0;
+	// symmetric-tile path (nb200_direct_sym.cuh)
+	void*			sym_tiles = nullptr;	// int2 {row block, column block} of this rank's tiles
+	real*			sym_prow = nullptr;		// [tiles][3][T] row sums
+	real*			sym_pcol = nullptr;		// [tiles][3][T] column sums
+	real*			sym_acc = nullptr;		// [shard][3][n_shard] reduced accelerations (+ [3][n_shard] receive block)
+	size_t			sym_ntiles = 0;
+	int				sym_edge = 0;
 	unsigned long long*	d_scalar = nullptr;	// device scratch: maxabs bits, walk counters (4 x u64)
 	unsigned long long*	h_scalar = nullptr;	// pinned mirror
 	bh_state*		bh = nullptr;
@@ -69,7 +76,8 @@ struct nb200_ctx
 	int			first_shard = 0;
 	size_t		n = 0;          // bodies
 	size_t		n_shard = 0;    // bodies per shard
-	size_t		n_pad = 0;      // packed source count incl. padding
+	size_t		n_pad = 0;      // packed source count incl. padding (multiple of the plain kernel's tile)
+	size_t		n_alloc = 0;    // allocated packed sources (multiple of the largest symmetric tile edge)
 	nccl_api*	nccl = nullptr;
 	void*		comm = nullptr; // ncclComm_t
 	std::unordered_set<const nb200_buf*>	live;
@@ -86,6 +94,9 @@ struct nb200_ctx
 	long long	opt_walk_block = 0;	// walk_mode
 	long long	opt_walk_threads = 0;
 	long long	opt_timing = 1;
+	long long	opt_direct_sym = -1;	// -1 auto, 0 off, 1 force
+	long long	opt_sym_tile = 0;		// tile edge override (multiple of 256)
+	long long	opt_sym_shape = 1;		// bodies per lane (row x column): 0: 8 x 1, 1: 4 x 2 (fastest measured), 2: 8 x 2, 3: 4 x 4
 };
 
 struct nb200_buf

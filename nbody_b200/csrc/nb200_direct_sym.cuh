@@ -1,0 +1,247 @@
+// nb200 -- symmetric (Newton's third law) all-pairs tiles for large N, FP64.
+//
+// The plain kernel (nb200_direct.cuh) evaluates every ORDERED pair: 17 FP64-pipe instructions per interaction.
+// Here every UNORDERED pair is evaluated once and applied to both bodies (a_i += m_j c d, a_j -= m_i c d):
+// 21 FP64-pipe instructions per two interactions. Same mathematics and the same exact MinDistance clamp as
+// nbody_data::force (nbody/nbody_data.cpp:35-44); only the order of the sums differs.
+//
+// Shape
+//   * the N x N interaction matrix is cut into T x T tiles (T = 4096 or 8192 bodies); only tiles on or above the
+//     diagonal are computed, one CTA (8 warps) per tile;
+//   * inside a tile every warp runs a systolic exchange: a lane keeps I "row" bodies with their accumulators in
+//     registers and J "column" bodies WITH THEIR accumulators; after each step (I x J pairs per lane) the column
+//     group moves to the next lane by warp shuffles, so after 32 steps the 32*I row bodies have met the 32*J column
+//     bodies and every column accumulator is back in its home lane -- no shared-memory traffic in the loop;
+//   * column sums of a tile are combined in shared memory, one column block per warp per phase (warps are kept
+//     nB/8 blocks apart and a block barrier separates phases), so the summation order is fixed;
+//   * each tile writes its row sums and column sums to scratch; direct_sym_reduce adds the <= 2N/T partials of a
+//     body in a fixed order. Results are therefore bit-reproducible run to run, like the plain kernel's;
+//   * diagonal tiles hold both (i,j) and (j,i): they are evaluated one-sided (row sums only).
+// With several ranks the tiles are dealt round-robin, every rank reduces its own tiles into a full-length partial
+// vector and one NCCL reduce-scatter leaves each rank with the accelerations of its own body shard.
+#ifndef NB200_DIRECT_SYM_CUH
+#define NB200_DIRECT_SYM_CUH
+
+#include "nb200_common.cuh"
+
+#if NB200_PRECISION == 2
+
+#define NB200_SYM_WARPS 8
+#define NB200_SYM_THREADS (32 * NB200_SYM_WARPS)
+
+__device__ __forceinline__ double sym_shfl(double v, int src_lane)
+{
+	int lo = __shfl_sync(0xffffffffu, __double2loint(v), src_lane);
+	int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src_lane);
+	return __hiloint2double(hi, lo);
+}
+
+// tile_rc[t] = {row block, column block} of the t-th tile this CTA grid works on
+template<int I, int J>
+__global__ void __launch_bounds__(NB200_SYM_THREADS, 1)
+direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, double* __restrict__ p_row,
+				 double* __restrict__ p_col, int tile_edge)
+{
+	extern __shared__ double colacc[];	// [3][tile_edge]
+	const int	T = tile_edge;
+	const int	lane = threadIdx.x & 31;
+	const int	warp = threadIdx.x >> 5;
+	const int2	rc = tile_rc[blockIdx.x];
+	const bool	diagonal = rc.x == rc.y;
+	const body4* __restrict__ rows = src + static_cast<size_t>(rc.x) * T;
+	const body4* __restrict__ cols = src + static_cast<size_t>(rc.y) * T;
+	double*		out_row = p_row + static_cast<size_t>(blockIdx.x) * 3 * T;
+	double*		out_col = p_col + static_cast<size_t>(blockIdx.x) * 3 * T;
+	const int	n_ablk = T / (32 * I);	// row blocks of the tile, dealt to the warps round-robin
+	const int	n_bblk = T / (32 * J);	// column blocks of the tile
+	const int	from = (lane + 31) & 31;	// the column group arrives from lane - 1
+
+	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	{
+		colacc[e] = 0;
+	}
+	__syncthreads();
+
+	for(int a0 = 0; a0 < n_ablk; a0 += NB200_SYM_WARPS)
+	{
+		// every warp runs every phase (the phase barrier is block-wide); warps without a row block just keep step
+		const int	ablk = a0 + warp;
+		const bool	active = ablk < n_ablk;
+		double xa[I], ya[I], za[I], ma[I], ax[I], ay[I], az[I];
+#pragma unroll
+		for(int k = 0; k < I; ++k)
+		{
+			const body4 b = rows[(active ? ablk : 0) * 32 * I + k * 32 + lane];
+			xa[k] = b.x; ya[k] = b.y; za[k] = b.z; ma[k] = b.m;
+			ax[k] = ay[k] = az[k] = 0;
+		}
+		// phase p: warp w owns column block (p + w * n_bblk / 8) mod n_bblk -- no two warps share a block in a phase
+		int		bblk = (warp * (n_bblk / NB200_SYM_WARPS)) % n_bblk;
+		body4	nxt[J];
+#pragma unroll
+		for(int q = 0; q < J; ++q)
+		{
+			nxt[q] = cols[bblk * 32 * J + q * 32 + lane];
+		}
+		for(int p = 0; p < n_bblk; ++p)
+		{
+			if(active)
+			{
+			double xb[J], yb[J], zb[J], mb[J], bx[J], by[J], bz[J];
+#pragma unroll
+			for(int q = 0; q < J; ++q)
+			{
+				xb[q] = nxt[q].x; yb[q] = nxt[q].y; zb[q] = nxt[q].z; mb[q] = nxt[q].m;
+				bx[q] = by[q] = bz[q] = 0;
+			}
+			const int	cur = bblk;
+			bblk = bblk + 1 == n_bblk ? 0 : bblk + 1;
+			if(p + 1 < n_bblk)
+			{
+				// prefetch the next phase's column bodies while this block rotates
+#pragma unroll
+				for(int q = 0; q < J; ++q)
+				{
+					nxt[q] = cols[bblk * 32 * J + q * 32 + lane];
+				}
+			}
+#pragma unroll 1
+			for(int step = 0; step < 32; ++step)
+			{
+#pragma unroll
+				for(int q = 0; q < J; ++q)
+				{
+#pragma unroll
+					for(int k = 0; k < I; ++k)
+					{
+						double	dx = xb[q] - xa[k];
+						double	dy = yb[q] - ya[k];
+						double	dz = zb[q] - za[k];
+						double	r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+						long long		bits = __double_as_longlong(r2);
+						const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8, exact clamp on the integer pipe
+						bits = bits < min_bits ? min_bits : bits;
+						r2 = __longlong_as_double(bits);
+						double	y0;
+						asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+						double	h = r2 * y0;
+						double	e = fma(-h, y0, 1.0);
+						double	pp = fma(e, 0.375, 0.5);
+						double	qq = y0 * e;
+						double	y = fma(qq, pp, y0);
+						double	y3 = (y * y) * y;
+						double	ca = mb[q] * y3;
+						double	cb = ma[k] * y3;
+						ax[k] = fma(dx, ca, ax[k]);
+						ay[k] = fma(dy, ca, ay[k]);
+						az[k] = fma(dz, ca, az[k]);
+						bx[q] = fma(-dx, cb, bx[q]);
+						by[q] = fma(-dy, cb, by[q]);
+						bz[q] = fma(-dz, cb, bz[q]);
+					}
+				}
+#pragma unroll
+				for(int q = 0; q < J; ++q)
+				{
+					xb[q] = sym_shfl(xb[q], from); yb[q] = sym_shfl(yb[q], from); zb[q] = sym_shfl(zb[q], from);
+					mb[q] = sym_shfl(mb[q], from);
+					bx[q] = sym_shfl(bx[q], from); by[q] = sym_shfl(by[q], from); bz[q] = sym_shfl(bz[q], from);
+				}
+			}
+			// 32 moves later every column body is home again, carrying the sum over this warp's 32*I row bodies
+			if(!diagonal)
+			{
+#pragma unroll
+				for(int q = 0; q < J; ++q)
+				{
+					const int c = cur * 32 * J + q * 32 + lane;
+					colacc[c] += bx[q];
+					colacc[T + c] += by[q];
+					colacc[2 * T + c] += bz[q];
+				}
+			}
+			}
+			__syncthreads();	// phase boundary: next phase another warp owns this column block
+		}
+		if(active)
+		{
+#pragma unroll
+			for(int k = 0; k < I; ++k)
+			{
+				const int r = ablk * 32 * I + k * 32 + lane;
+				out_row[r] = ax[k];
+				out_row[T + r] = ay[k];
+				out_row[2 * T + r] = az[k];
+			}
+		}
+	}
+	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	{
+		out_col[e] = colacc[e];
+	}
+}
+
+// Index of tile (r, c), c >= r, in the row-major enumeration of the upper triangle of an S x S grid.
+__host__ __device__ __forceinline__ long long sym_tile_id(int r, int c, int S)
+{
+	return static_cast<long long>(r) * S - static_cast<long long>(r) * (r - 1) / 2 + (c - r);
+}
+
+// acc[comp][body] = sum of the partials of every tile of THIS rank that touches the body's block, in a fixed order:
+// column sums of tiles (a, blk), a < blk, ascending a; then row sums of tiles (blk, c), c >= blk, ascending c.
+// out layout: [shard][comp][n_shard] over all N bodies (the send buffer of the reduce-scatter; [3][N] for one shard).
+__global__ void __launch_bounds__(256) direct_sym_reduce(const double* __restrict__ p_row, const double* __restrict__ p_col,
+														 double* __restrict__ out, size_t n_bodies, size_t n_shard,
+														 int tile_edge, int S, int rank, int nranks)
+{
+	const size_t body = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(body >= n_bodies)
+	{
+		return;
+	}
+	double			acc[3] = {0, 0, 0};
+	{
+		const int		T = tile_edge;
+		const int		blk = static_cast<int>(body / T);
+		const int		off = static_cast<int>(body % T);
+		for(int a = 0; a < blk; ++a)
+		{
+			const long long id = sym_tile_id(a, blk, S);
+			if(id % nranks == rank)
+			{
+				const double* p = p_col + static_cast<size_t>(id / nranks) * 3 * T + off;
+				acc[0] += p[0]; acc[1] += p[T]; acc[2] += p[2 * T];
+			}
+		}
+		for(int c = blk; c < S; ++c)
+		{
+			const long long id = sym_tile_id(blk, c, S);
+			if(id % nranks == rank)
+			{
+				const double* p = p_row + static_cast<size_t>(id / nranks) * 3 * T + off;
+				acc[0] += p[0]; acc[1] += p[T]; acc[2] += p[2 * T];
+			}
+		}
+	}
+	const size_t shard = body / n_shard, local = body % n_shard;
+	double* o = out + shard * 3 * n_shard + local;
+	o[0] = acc[0];
+	o[n_shard] = acc[1];
+	o[2 * n_shard] = acc[2];
+}
+
+// f = (v, a) for the local shard from an acceleration block laid out [3][n_shard]
+__global__ void __launch_bounds__(256) direct_sym_finish(const double* __restrict__ acc, const double* __restrict__ y,
+														 double* __restrict__ f, size_t n_shard)
+{
+	const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(e >= 3 * n_shard)
+	{
+		return;
+	}
+	f[e] = y[3 * n_shard + e];
+	f[3 * n_shard + e] = acc[e];
+}
+
+#endif // NB200_PRECISION == 2
+#endif // NB200_DIRECT_SYM_CUH

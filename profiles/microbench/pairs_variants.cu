@@ -206,6 +206,114 @@ __global__ void __launch_bounds__(THREADS, MINB) pairs_fast(const body4* __restr
 	}
 }
 
+// ---- symmetric (Newton's third law) systolic warp tile --------------------------------------------------
+// Each lane keeps I "A" bodies (+ accumulators) and J "B" bodies (+ accumulators). Per step the lane evaluates its
+// I x J unordered pairs once (21 FP64 instr) and updates BOTH sides; then the B group (positions, mass, accumulators)
+// moves to the next lane by shuffles. After 32 steps every A body has met every B body of the 32*J block.
+__device__ __forceinline__ double shfl_d(double v, int src)
+{
+	int lo = __shfl_sync(0xffffffffu, __double2loint(v), src);
+	int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src);
+	return __hiloint2double(hi, lo);
+}
+
+template<int I, int J>
+__global__ void __launch_bounds__(THREADS) pairs_sym(const body4* __restrict__ src, double* __restrict__ out, int n, int nb_blocks_per_warp)
+{
+	const int lane = threadIdx.x & 31;
+	const int warp = (blockIdx.x * THREADS + threadIdx.x) >> 5;
+	const int a0 = (warp * 32 * I) % n;
+	double xa[I], ya[I], za[I], ma[I], ax[I], ay[I], az[I];
+#pragma unroll
+	for(int k = 0; k < I; ++k)
+	{
+		body4 b = src[(a0 + k * 32 + lane) % n];
+		xa[k] = b.x; ya[k] = b.y; za[k] = b.z; ma[k] = b.m; ax[k] = ay[k] = az[k] = 0;
+	}
+	const int next = (lane + 31) & 31;   // receive from lane-1
+	for(int blk = 0; blk < nb_blocks_per_warp; ++blk)
+	{
+		const int b0 = ((warp * 7 + blk) * 32 * J) % n;
+		double xb[J], yb[J], zb[J], mb[J], bx[J], by[J], bz[J];
+#pragma unroll
+		for(int q = 0; q < J; ++q)
+		{
+			body4 b = src[(b0 + q * 32 + lane) % n];
+			xb[q] = b.x; yb[q] = b.y; zb[q] = b.z; mb[q] = b.m; bx[q] = by[q] = bz[q] = 0;
+		}
+#pragma unroll 1
+		for(int step = 0; step < 32; ++step)
+		{
+#pragma unroll
+			for(int q = 0; q < J; ++q)
+			{
+#pragma unroll
+				for(int k = 0; k < I; ++k)
+				{
+					double dx = xb[q] - xa[k], dy = yb[q] - ya[k], dz = zb[q] - za[k];
+					double r2 = clamp_int(fma(dz, dz, fma(dy, dy, dx * dx)));
+					double y0 = seed_rsqrt(r2);
+					double h = r2 * y0;
+					double e = fma(-h, y0, 1.0);
+					double p = fma(e, 0.375, 0.5);
+					double qq = y0 * e;
+					double y = fma(qq, p, y0);
+					double y3 = (y * y) * y;
+					double ca = mb[q] * y3, cb = ma[k] * y3;
+					ax[k] = fma(dx, ca, ax[k]); ay[k] = fma(dy, ca, ay[k]); az[k] = fma(dz, ca, az[k]);
+					bx[q] = fma(-dx, cb, bx[q]); by[q] = fma(-dy, cb, by[q]); bz[q] = fma(-dz, cb, bz[q]);
+				}
+			}
+#pragma unroll
+			for(int q = 0; q < J; ++q)
+			{
+				xb[q] = shfl_d(xb[q], next); yb[q] = shfl_d(yb[q], next); zb[q] = shfl_d(zb[q], next); mb[q] = shfl_d(mb[q], next);
+				bx[q] = shfl_d(bx[q], next); by[q] = shfl_d(by[q], next); bz[q] = shfl_d(bz[q], next);
+			}
+		}
+#pragma unroll
+		for(int q = 0; q < J; ++q)
+		{
+			int j = (b0 + q * 32 + lane) % n;
+			atomicAdd(out + j, bx[q]); atomicAdd(out + n + j, by[q]); atomicAdd(out + 2 * n + j, bz[q]);
+		}
+	}
+#pragma unroll
+	for(int k = 0; k < I; ++k)
+	{
+		int i = (a0 + k * 32 + lane) % n;
+		atomicAdd(out + i, ax[k]); atomicAdd(out + n + i, ay[k]); atomicAdd(out + 2 * n + i, az[k]);
+	}
+}
+
+template<int I, int J>
+void run_sym(const char* name, const body4* src, double* out, int n)
+{
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	// 148*8 CTAs of 4 warps; every warp meets `nbw` B blocks: unordered pairs = warps * (32 I) * (32 J) * nbw
+	int grid = 148 * 8, nbw = 256;
+	pairs_sym<I, J><<<grid, THREADS>>>(src, out, n, 4);
+	cudaDeviceSynchronize();
+	float best = 1e30f;
+	for(int r = 0; r < 3; ++r)
+	{
+		cudaEventRecord(e0);
+		pairs_sym<I, J><<<grid, THREADS>>>(src, out, n, nbw);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if(ms < best) { best = ms; }
+	}
+	cudaFuncAttributes fa;
+	cudaFuncGetAttributes(&fa, pairs_sym<I, J>);
+	double unordered = (double)grid * 4 * (32.0 * I) * (32.0 * J) * nbw;
+	printf("%-40s regs %3d  %8.3f ms  %7.2f G unordered pairs/s = %7.2f G interactions/s\n", name, fa.numRegs, best,
+		   unordered / best / 1e6, 2 * unordered / best / 1e6);
+}
+
 template<int IPT, int UNR, int MINB, int VAR>
 void run_fast(const char* name, const body4* src, double* out, int n)
 {
@@ -275,6 +383,12 @@ int main(int argc, char** argv)
 	cudaMalloc(&out, 3 * n * sizeof(double));
 	cudaMemcpy(d, h, n * sizeof(body4), cudaMemcpyHostToDevice);
 	run<4, 4, 1, 0>("ipt4 unr4 intclamp (current)", d, out, n);
+	run_sym<4, 4>("SYM I4 J4", d, out, n);
+	run_sym<4, 2>("SYM I4 J2", d, out, n);
+	run_sym<8, 2>("SYM I8 J2", d, out, n);
+	run_sym<8, 1>("SYM I8 J1", d, out, n);
+	run_sym<6, 2>("SYM I6 J2", d, out, n);
+	run_sym<2, 2>("SYM I2 J2", d, out, n);
 	run_fast<4, 4, 1, 0>("FAST ipt4 unr4", d, out, n);
 	run_fast<4, 4, 1, 1>("FAST ipt4 unr4 junk-lo seed", d, out, n);
 	run_fast<4, 4, 1, 3>("FAST ipt4 unr4 junk-lo NOFLAG", d, out, n);

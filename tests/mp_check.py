@@ -29,9 +29,13 @@ def main():
     y, m = universe(n)
     orc = Oracle("f64")
     results = {}
-    for kind, kw in (("direct", {}), ("bh", dict(distance_to_node_radius_ratio=3.1623))):
+    for label, kind, kw, opts in (("direct", "direct", {}, ()),
+                                  ("direct-symmetric", "direct", {}, (("direct_symmetric", 1), ("direct_sym_tile", 2048))),
+                                  ("bh", "bh", dict(distance_to_node_radius_ratio=3.1623), ())):
         uid = dist.exchange_unique_id(lambda: new_unique_id("f64"))
         e = Engine(devices=[local], rank=rank, nranks=world, uid=uid, kind=kind, **kw)
+        for k, v in opts:
+            e.set_option(k, v)
         assert e.shards() == (world, rank)
         assert e.init(y, m), e.last_error()
         f = e.create_buffer(e.get_y().size())
@@ -62,7 +66,7 @@ def main():
                 tree = orc.heap_build(y, m, 3.1623)
                 want, _, _ = orc.fcompute_bh(y, m, tree)
                 assert rel_err_per_body(got, want, n) <= 1e-12
-            print("mp_check %s ok: %d ranks, vs single-GPU rel err %.2e" % (kind, world, err), flush=True)
+            print("mp_check %s ok: %d ranks, vs single-GPU rel err %.2e" % (label, world, err), flush=True)
     dist.barrier()
     print("rank %d done" % rank, flush=True)
 

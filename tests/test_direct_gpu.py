@@ -151,4 +151,49 @@ def test_multi_process_nccl_two_ranks():
            "--master-port", "29517", os.path.join(root, "tests", "mp_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "mp_check direct ok" in out.stdout and "mp_check bh ok" in out.stdout
+    assert "mp_check direct ok" in out.stdout and "mp_check bh ok" in out.stdout and "mp_check direct-symmetric ok" in out.stdout
+
+
+# ---- symmetric (Newton's third law) tile path: automatic for N >= 196,608, forced here on small systems ----------
+@pytest.mark.parametrize("n,tile,shape", [(4096, 1024, 0), (8192, 2048, 0), (5000, 1024, 0), (4096, 1024, 1), (2048, 256, 0),
+                                          (3000, 512, 1)])
+def test_direct_symmetric_tiles_vs_oracle(oracle64, n, tile, shape):
+    """Every unordered pair evaluated once and applied to both bodies; ragged N pads the last tile with zero-mass
+    bodies; diagonal tiles are one-sided. Same 1e-12 gate as the plain kernel."""
+    rng = np.random.RandomState(n + tile)
+    y = rng.uniform(-50, 50, 6 * n)
+    m = rng.uniform(0.1, 2.0, n)
+    y[0:2] = y[2]                      # bodies 0, 1, 2 share an x coordinate ...
+    y[n:n + 2] = y[n + 2]
+    y[2 * n] = y[2 * n + 2]            # ... and bodies 0 and 2 coincide entirely (clamped pair)
+    y[2 * n + 1] = y[2 * n + 2] + 5e-5
+    opts = (("direct_symmetric", 1), ("direct_sym_tile", tile), ("direct_sym_shape", shape))
+    f = run_direct(y, m, options=opts)
+    ref = oracle64.fcompute_openmp(y, m)
+    assert np.array_equal(f[:3 * n], y[3 * n:])
+    assert np.all(np.isfinite(f))
+    assert rel_err_per_body(f, ref, n) <= TOL64
+    plain = run_direct(y, m, options=(("direct_symmetric", 0),))
+    assert rel_err_per_body(f, plain, n) <= 1e-13
+    again = run_direct(y, m, options=opts)
+    assert np.array_equal(f, again)                     # fixed summation order: bit-reproducible
+
+
+def test_direct_symmetric_golden_universe():
+    g = load_golden_npz("g1_n2048")
+    f = run_direct(g["y"], g["mass"], options=(("direct_symmetric", 1), ("direct_sym_tile", 512)))
+    assert rel_err_per_body(f, g["f_openmp"], 2048) <= TOL64
+    assert rel_err_per_body(f, g["f_block"], 2048) <= TOL64
+
+
+def test_direct_symmetric_is_the_large_n_default(oracle64):
+    """N = 262,144 takes the symmetric path automatically (tile 4096): sampled check + third-law property."""
+    n = 262144
+    y, m = universe(n)
+    f = run_direct(y, m).reshape(6, n)
+    t = np.unique(np.concatenate([[0, n // 2, n - 1], np.random.RandomState(9).randint(0, n, 125)]))
+    ref = oracle64.accel_subset(y, m, t)
+    assert rel_err_per_body(f[3:, t], ref, t.size) <= TOL64
+    force = (f[3:] * m[None, :]).sum(axis=1)
+    scale = np.abs(f[3:] * m[None, :]).sum(axis=1)
+    assert np.all(np.abs(force) <= 1e-11 * scale)
