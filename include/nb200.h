@@ -174,6 +174,9 @@ unsigned long long nb200_launch_count(const nb200_ctx* ctx);
  * out[0] = pack + gather, out[1] = tree build / refresh (BH only),
  * out[2] = force kernel (pairs or walk), out[3] = reduce/epilogue. Synchronises. */
 int nb200_last_fcompute_ms(nb200_ctx* ctx, float out[4]);
+/* Which kernel family the most recent nb200_fcompute_direct used: 0 = ordered-pair kernel (direct_pairs),
+ * otherwise the tile edge of the symmetric-tile kernel (direct_sym_tiles). */
+int nb200_last_direct_path(const nb200_ctx* ctx);
 /* CUDA-event stopwatch on lane 0's stream (the stream the kernels run on): nb200_mark records event
  * `slot` (0..7); nb200_elapsed_ms synchronises on slot b and returns the device time from a to b. */
 int nb200_mark(nb200_ctx* ctx, int slot);

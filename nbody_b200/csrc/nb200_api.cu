@@ -771,9 +771,11 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 #if NB200_PRECISION == 2
 	if(const int edge = sym_tile_edge(ctx))
 	{
+		ctx->last_direct_path = edge;
 		return sym_fcompute(ctx, y, f, edge);
 	}
 #endif
+	ctx->last_direct_path = 0;
 
 	const int	n_tiles = static_cast<int>(ctx->n_pad / NB200_DIRECT_TILE);
 	const int	sms = ctx->lanes[0].sm_count;
@@ -1133,6 +1135,11 @@ NB200_API int nb200_last_fcompute_ms(nb200_ctx* ctx, float out[4])
 		}
 	}
 	return NB200_OK;
+}
+
+NB200_API int nb200_last_direct_path(const nb200_ctx* ctx)
+{
+	return ctx != nullptr ? ctx->last_direct_path : 0;
 }
 
 NB200_API int nb200_mark(nb200_ctx* ctx, int slot)

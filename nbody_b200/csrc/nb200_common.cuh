@@ -82,6 +82,7 @@ struct nb200_ctx
 	void*		comm = nullptr; // ncclComm_t
 	std::unordered_set<const nb200_buf*>	live;
 	unsigned long long	launches = 0;
+	int			last_direct_path = 0;
 	std::string	err;
 	// Barnes-Hut configuration
 	real		bh_ratio = 10;

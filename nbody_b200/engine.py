@@ -82,6 +82,7 @@ def load_library(precision="f64"):
     sig("nb200_clamp", i32, vp, vp, real)
     sig("nb200_launch_count", ull, vp)
     sig("nb200_last_fcompute_ms", i32, vp, P(C.c_float))
+    sig("nb200_last_direct_path", i32, vp)
     sig("nb200_mark", i32, vp, i32)
     sig("nb200_elapsed_ms", i32, vp, i32, i32, P(C.c_float))
     sig("nb200_probe_fma_peak", i32, vp, C.c_double, P(C.c_double))
@@ -453,6 +454,10 @@ class Engine:
         out = (C.c_float * 4)()
         self.lib.nb200_last_fcompute_ms(self.ctx, out)
         return dict(pack_gather=out[0], tree=out[1], force=out[2], reduce=out[3])
+
+    def last_direct_path(self):
+        """0 = ordered-pair kernel, otherwise the tile edge of the symmetric-tile kernel."""
+        return int(self.lib.nb200_last_direct_path(self.ctx))
 
     def mark(self, slot):
         """Record CUDA event `slot` on the engine's stream (device-side stopwatch)."""
