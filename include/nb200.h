@@ -167,6 +167,13 @@ int nb200_fmaxabs(nb200_ctx* ctx, const nb200_buf* a, nb200_real* result);
 /* Periodic wrap of the three position rows into [-b, b] (kclamp_coord, impl.cu:724-747). */
 int nb200_clamp(nb200_ctx* ctx, nb200_buf* y, nb200_real b);
 
+/* ---- conservation report (device-side nbody_data::print_statistics sums) ------------------------
+ * From a state vector y: out[0..2] total impulse sum m v, out[3..5] impulse moment sum r x m v, out[6] kinetic energy
+ * sum m v^2 / 2, out[7] potential energy -1/2 sum_{i != j, r2 >= 1e-8} m_i m_j / r (0 unless with_energy; O(N^2) on the
+ * device instead of the reference's single-threaded host loop, nbody_data.cpp:81-87), out[8..10] mass centre.
+ * Always double, host-visible on return. With nranks > 1 every rank receives the global sums. */
+int nb200_statistics(nb200_ctx* ctx, const nb200_buf* y, int with_energy, double out[11]);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of nb200 kernels launched since creation (all lanes). */
 unsigned long long nb200_launch_count(const nb200_ctx* ctx);

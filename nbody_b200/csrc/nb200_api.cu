@@ -18,6 +18,7 @@
 #include "nb200_direct_sym.cuh"
 #include "nb200_stateops.cuh"
 #include "nb200_bh.cuh"
+#include "nb200_stats.cuh"
 
 #define NB200_API extern "C" __attribute__((visibility("default")))
 
@@ -1110,6 +1111,82 @@ NB200_API int nb200_clamp(nb200_ctx* ctx, nb200_buf* y, nb200_real b)
 		ew_clamp<<<static_cast<unsigned>((count3 + NB200_EW_THREADS - 1) / NB200_EW_THREADS), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(y, i), b, count3);
 		LAUNCHED(ctx);
 	}
+	return NB200_OK;
+}
+
+// ---- conservation report ----------------------------------------------------------------------------
+NB200_API int nb200_statistics(nb200_ctx* ctx, const nb200_buf* y, int with_energy, double out[11])
+{
+	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "statistics: y is not a buffer of this context"); }
+	if(ctx->n == 0 || !y->sharded) { return fail(ctx, NB200_ERR_ARG, "statistics: y must be a state vector of 6*N elements"); }
+	if(with_energy)
+	{
+		int rc = pack_and_gather(ctx, y);	// the potential needs every body's position on every shard
+		if(rc != NB200_OK) { return rc; }
+	}
+	const int	n_tiles = static_cast<int>(ctx->n_pad / NB200_DIRECT_TILE);
+	double		total[NB200_STATS_LINEAR + 1] = {0};
+	std::vector<double*> scratch(ctx->lanes.size(), nullptr);
+	std::vector<double*> host(ctx->lanes.size(), nullptr);
+	int status = NB200_OK;
+	for(size_t li = 0; li < ctx->lanes.size() && status == NB200_OK; ++li)
+	{
+		nb200_lane& l = ctx->lanes[li];
+		cudaSetDevice(l.dev);
+		const int lin_blocks = std::max(1, std::min<int>(l.sm_count * 4, static_cast<int>((ctx->n_shard + NB200_STATS_THREADS - 1) / NB200_STATS_THREADS)));
+		const int pot_blocks = with_energy ? static_cast<int>((ctx->n_shard + NB200_STATS_THREADS - 1) / NB200_STATS_THREADS) : 0;
+		const size_t elems = static_cast<size_t>(lin_blocks) * NB200_STATS_LINEAR + pot_blocks + NB200_STATS_LINEAR + 1;
+		if(cudaMalloc(&scratch[li], elems * sizeof(double)) != cudaSuccess || cudaMallocHost(&host[li], (NB200_STATS_LINEAR + 1) * sizeof(double)) != cudaSuccess)
+		{
+			cudaGetLastError();
+			status = fail(ctx, NB200_ERR_ALLOC, "statistics: scratch allocation failed");
+			break;
+		}
+		double* lin = scratch[li];
+		double* pot = lin + static_cast<size_t>(lin_blocks) * NB200_STATS_LINEAR;
+		double* res = pot + pot_blocks;
+		const size_t first = static_cast<size_t>(l.shard) * ctx->n_shard;
+		stats_linear<<<lin_blocks, NB200_STATS_THREADS, 0, l.stream>>>(lane_ptr(y, li), l.mass, ctx->n_shard, first, lin);
+		++ctx->launches;
+		if(with_energy)
+		{
+			stats_potential<<<pot_blocks, NB200_STATS_THREADS, 0, l.stream>>>(l.src, ctx->n_shard, first, n_tiles, pot);
+			++ctx->launches;
+		}
+		stats_finish<<<1, 32, 0, l.stream>>>(lin, lin_blocks, pot, pot_blocks, res);
+		++ctx->launches;
+		if(ctx->nranks > 1 && ctx->nccl->AllReduce(res, res, NB200_STATS_LINEAR + 1, ncclFloat64, ncclSum, static_cast<ncclComm_t>(ctx->comm), l.stream) != ncclSuccess)
+		{
+			status = fail(ctx, NB200_ERR_NCCL, "statistics: ncclAllReduce failed");
+			break;
+		}
+		if(cudaMemcpyAsync(host[li], res, (NB200_STATS_LINEAR + 1) * sizeof(double), cudaMemcpyDeviceToHost, l.stream) != cudaSuccess)
+		{
+			status = fail(ctx, NB200_ERR_CUDA, "statistics: %s", cudaGetErrorString(cudaGetLastError()));
+		}
+	}
+	for(size_t li = 0; li < ctx->lanes.size(); ++li)
+	{
+		nb200_lane& l = ctx->lanes[li];
+		cudaSetDevice(l.dev);
+		if(status == NB200_OK && cudaStreamSynchronize(l.stream) != cudaSuccess)
+		{
+			status = fail(ctx, NB200_ERR_CUDA, "statistics: %s", cudaGetErrorString(cudaGetLastError()));
+		}
+		if(status == NB200_OK && host[li] != nullptr)
+		{
+			for(int q = 0; q <= NB200_STATS_LINEAR; ++q) { total[q] += host[li][q]; }	// lanes in shard order: fixed
+		}
+		if(scratch[li]) { cudaFree(scratch[li]); }
+		if(host[li]) { cudaFreeHost(host[li]); }
+	}
+	if(status != NB200_OK) { return status; }
+	// linear partial layout: Px Py Pz Lx Ly Lz 2Ekin Cx Cy Cz M
+	for(int q = 0; q < 6; ++q) { out[q] = total[q]; }
+	out[6] = total[6] / 2;
+	out[7] = with_energy ? -total[NB200_STATS_LINEAR] / 2 : 0;
+	for(int q = 0; q < 3; ++q) { out[8 + q] = total[7 + q] / total[10]; }
 	return NB200_OK;
 }
 

@@ -80,6 +80,7 @@ def load_library(precision="f64"):
     sig("nb200_fmaddn_corr", i32, vp, vp, vp, P(vp), vp, sz)
     sig("nb200_fmaxabs", i32, vp, vp, P(real))
     sig("nb200_clamp", i32, vp, vp, real)
+    sig("nb200_statistics", i32, vp, vp, i32, P(C.c_double))
     sig("nb200_launch_count", ull, vp)
     sig("nb200_last_fcompute_ms", i32, vp, P(C.c_float))
     sig("nb200_last_direct_path", i32, vp)
@@ -442,6 +443,18 @@ class Engine:
         if self._check(self.lib.nb200_fmaxabs(self.ctx, ha, C.byref(out)), "fmaxabs") != 0:
             return default
         return self.dtype.type(out.value)
+
+    # ---- conservation report (device-side print_statistics sums) ---------------
+    def statistics(self, y=None, with_energy=True):
+        """dict(P[3], L[3], Ekin, Epot, C[3]) of the state vector `y` (default: get_y()); see nb200_statistics."""
+        hy = self._h(y if y is not None else self._y, "statistics", "y")
+        if hy is None:
+            return None
+        out = (C.c_double * 11)()
+        if self._check(self.lib.nb200_statistics(self.ctx, hy, 1 if with_energy else 0, out), "statistics") != 0:
+            return None
+        v = np.array(out[:], dtype=np.float64)
+        return dict(P=v[0:3], L=v[3:6], Ekin=v[6], Epot=v[7], C=v[8:11])
 
     # ---- instrumentation ------------------------------------------------------
     def synchronize(self):

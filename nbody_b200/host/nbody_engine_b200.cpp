@@ -528,6 +528,18 @@ void nbody_engine_b200::set_use_nccl(bool active)
 	Q_UNUSED(active);
 }
 
+bool nbody_engine_b200::statistics(const memory* _y, bool with_energy, double out[11])
+{
+	nb200_buf*	y = d->handle(_y, "y");
+	if(y == nullptr)
+	{
+		return false;
+	}
+	int rc = nb200_statistics(d->m_ctx, y, with_energy ? 1 : 0, out);
+	d->check(rc, "statistics");
+	return rc == NB200_OK;
+}
+
 unsigned long long nbody_engine_b200::launch_count() const
 {
 	return nb200_launch_count(d->m_ctx);

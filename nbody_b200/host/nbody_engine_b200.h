@@ -66,6 +66,9 @@ public:
 	void set_block_size(int block_size);
 	//! Single-process lanes exchange shards by peer copies; NCCL is used by the one-process-per-GPU mode only
 	void set_use_nccl(bool);
+	//! Device-side conservation sums of nbody_data::print_statistics (nbody_data.cpp:57-103) for a state vector:
+	//! out = {P[3], L[3], Ekin, Epot, mass centre[3]}; Epot (O(N^2), on the GPU) only when with_energy. False on error.
+	bool statistics(const memory* y, bool with_energy, double out[11]);
 	//! Kernels launched so far (instrumentation)
 	unsigned long long launch_count() const;
 	//! Block until all queued device work has finished

@@ -1,0 +1,31 @@
+import sys, os
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+os.environ['NBREF_QUIET']='1'
+import numpy as np
+from nbody_b200 import Engine
+rng = np.random.RandomState(0)
+n = 2048
+y = rng.uniform(-50, 50, 6*n); m = rng.uniform(0.1, 2, n)
+for opts in ((), (("direct_symmetric",1),("direct_sym_tile",512)), (("direct_symmetric",1),("direct_sym_tile",256),("direct_sym_shape",0))):
+    with Engine(devices="0,0") if not opts else Engine() as e:
+        for k,v in opts: e.set_option(k,v)
+        assert e.init(y, m)
+        f = e.create_buffer(e.get_y().size())
+        e.fcompute(0, e.get_y(), f)
+        ks = e.create_buffers(e.get_y().size(), 3)
+        for k in ks: e.copy_buffer(k, f)
+        e.fmaddn(f, e.get_y(), ks, np.array([0.1, 0.0, 0.3]))
+        e.fmaddn_corr(f, ks[0], ks[1:], np.array([0.5, 0.25]))
+        print(opts, e.fmaxabs(f))
+with Engine(kind="bh", devices="0,0") as e:
+    assert e.init(y, m)
+    f = e.create_buffer(e.get_y().size())
+    e.fcompute(0, e.get_y(), f)
+    print("bh", e.fmaxabs(f))
+n = 4096
+y = rng.uniform(-50, 50, 6*n); m = rng.uniform(0.1, 2, n)
+with Engine(kind="bh") as e:
+    assert e.init(y, m)
+    f = e.create_buffer(e.get_y().size())
+    e.fcompute(0, e.get_y(), f)
+    print("bh4096", e.fmaxabs(f))
