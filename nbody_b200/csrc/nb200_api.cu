@@ -663,8 +663,14 @@ namespace {
 int sym_tile_edge(const nb200_ctx* ctx)
 {
 	if(ctx->lanes.size() != 1 || ctx->opt_direct_sym == 0) { return 0; }
-	if(ctx->opt_direct_sym < 0 && ctx->n < 196608) { return 0; }	// too few tiles to fill 148 SMs
-	long long edge = ctx->opt_sym_tile > 0 ? ctx->opt_sym_tile : (ctx->n >= 786432 ? 8192 : 4096);
+	if(ctx->opt_direct_sym < 0 && ctx->n < 32768) { return 0; }	// too few tiles to fill 148 SMs
+	// automatic edge: ~N/128 (>= 8000 equal tiles), at most 8192 (192 KB of column sums; scratch 24 N^2 / T bytes)
+	long long edge = ctx->opt_sym_tile;
+	if(edge <= 0)
+	{
+		edge = 1024;	// 8 row blocks of 128 bodies: the smallest tile that keeps all 8 warps busy
+		while(edge * 2 <= static_cast<long long>(ctx->n / 128) && edge < 8192) { edge *= 2; }
+	}
 	// 8 column blocks per phase round, 32*J bodies each; 32*I bodies per row block
 	const long long unit = ctx->opt_sym_shape == 3 ? 1024 : (ctx->opt_sym_shape >= 1 ? 512 : 256);
 	if(edge % unit != 0 || edge % 256 != 0 || edge > 8192) { return 0; }

@@ -154,7 +154,7 @@ def test_multi_process_nccl_two_ranks():
     assert "mp_check direct ok" in out.stdout and "mp_check bh ok" in out.stdout and "mp_check direct-symmetric ok" in out.stdout
 
 
-# ---- symmetric (Newton's third law) tile path: automatic for N >= 196,608, forced here on small systems ----------
+# ---- symmetric (Newton's third law) tile path: automatic for N >= 32,768, forced here on small systems ------------
 @pytest.mark.parametrize("n,tile,shape", [(4096, 1024, 0), (8192, 2048, 0), (5000, 1024, 0), (4096, 1024, 1), (2048, 256, 0),
                                           (3000, 512, 1)])
 def test_direct_symmetric_tiles_vs_oracle(oracle64, n, tile, shape):
@@ -187,9 +187,15 @@ def test_direct_symmetric_golden_universe():
 
 
 def test_direct_symmetric_is_the_large_n_default(oracle64):
-    """N = 262,144 takes the symmetric path automatically (tile 4096): sampled check + third-law property."""
+    """N = 262,144 takes the symmetric path automatically (tile 2048): sampled check + third-law property."""
     n = 262144
     y, m = universe(n)
+    from nbody_b200 import Engine
+    with Engine() as e:
+        assert e.init(y, m)
+        fb = e.create_buffer(e.get_y().size())
+        e.fcompute(0.0, e.get_y(), fb)
+        assert e.last_direct_path() == 2048
     f = run_direct(y, m).reshape(6, n)
     t = np.unique(np.concatenate([[0, n // 2, n - 1], np.random.RandomState(9).randint(0, n, 125)]))
     ref = oracle64.accel_subset(y, m, t)
