@@ -350,6 +350,37 @@ __device__ __forceinline__ void store_f(const real* __restrict__ y, real* __rest
 	f[5 * n_shard + li] = az;
 }
 
+// Accepted node: same force form as the direct kernel, reusing the separation d = me - node and d2 of the
+// acceptance test (clamp applied after the test, as in kfcompute_heap_bh_stackless, impl.cu:399-413).
+// a += m (node - me) / r^3  ==  a -= m d / r^3
+__device__ __forceinline__ void node_force_from_test(real dx, real dy, real dz, real d2, real m, real& ax, real& ay, real& az)
+{
+#if NB200_PRECISION == 2
+	long long		bits = __double_as_longlong(d2);
+	const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8
+	bits = bits < min_bits ? min_bits : bits;
+	const double	r2 = __longlong_as_double(bits);
+	double	y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+	double	h = r2 * y0;
+	double	e = fma(-h, y0, 1.0);
+	double	p = fma(e, 0.375, 0.5);
+	double	q = y0 * e;
+	double	yv = fma(q, p, y0);
+	double	c = (yv * yv) * (m * yv);
+	ax = fma(-dx, c, ax);
+	ay = fma(-dy, c, ay);
+	az = fma(-dz, c, az);
+#else
+	const float	r2 = fmaxf(d2, NB200_MIN_DISTANCE);
+	float	yv = rsqrtf(r2);
+	float	c = (yv * yv) * (m * yv);
+	ax = fmaf(-dx, c, ax);
+	ay = fmaf(-dy, c, ay);
+	az = fmaf(-dz, c, az);
+#endif
+}
+
 // one thread per target, independent stackless walks (the reference kernel's shape)
 __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 													   const int* __restrict__ body_n, const int* __restrict__ own_leaf,
@@ -367,12 +398,12 @@ __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ 
 	do
 	{
 		const node4	nd = load_node(xyzr, curr);
-		real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
-		real d2 = dx * dx + dy * dy + dz * dz;
+		const real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
+		const real d2 = dx * dx + dy * dy + dz * dz;	// same expression as bh_walk_warp (see the note there)
 		++visits;
 		if(d2 > nd.w)
 		{
-			node_force(me.x, me.y, me.z, nd, nmass[curr], ax, ay, az);
+			node_force_from_test(dx, dy, dz, d2, nmass[curr], ax, ay, az);
 			++inter;
 			curr = heap_skip_idx(curr);
 		}
@@ -395,6 +426,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 }
 
 // one warp per 32 consecutive targets, warp-uniform walk over the union of the lanes' traversals
+template<bool STATS>
 __global__ void __launch_bounds__(256) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 													 const int* __restrict__ body_n, const int* __restrict__ own_leaf,
 													 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
@@ -404,6 +436,7 @@ __global__ void __launch_bounds__(256) bh_walk_warp(const node4* __restrict__ xy
 	const bool	live = t < n_targets;
 	const int	tc = live ? t : n_targets - 1;	// idle lanes shadow the last target and never store
 	const int	leaf = n + (own_leaf != nullptr ? own_leaf[tc] : tc);
+	const int	tree_size = 2 * n;
 	const node4	me = load_node(xyzr, leaf);
 	real		ax = 0, ay = 0, az = 0;
 	unsigned	visits = 0, inter = 0;
@@ -415,39 +448,34 @@ __global__ void __launch_bounds__(256) bh_walk_warp(const node4* __restrict__ xy
 		const node4	nd = load_node(xyzr, curr);	// same address in every lane: one broadcast transaction
 		const int	skip = heap_skip_idx(curr);	// one BREV + FLO per visit, shared by the sleeping rule and the step
 		const int	child = curr << 1;
-#ifdef NB200_BH_PREFETCH
-		if(child < 2 * n)
-		{
-			// both children share one 64-byte block (measured: no gain on B200 -- the walk is issue-bound, not latency-bound)
-			prefetch_l1(xyzr + child);
-		}
-#endif
 		awake = awake || (curr == resume);
-		real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
-		real d2 = dx * dx + dy * dy + dz * dz;
-		const bool far = d2 > nd.w;
-		const bool accept = awake && far;
-		const bool open = awake && !far;
-		visits += awake ? 1u : 0u;
+		const real	dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
+		// left to the compiler's contraction on purpose: this form rounds like the reference's (v1 - cm).norm() built
+		// with gcc -O3, so knife-edge decisions (d2 == radius_sqr up to an ulp, e.g. an equal-mass pair at ratio 1)
+		// fall the same way as in simple_bh (tests compare visit counts with the CPU walk)
+		const real	d2 = dx * dx + dy * dy + dz * dz;
+		const bool	accept = awake && (d2 > nd.w);
+		const bool	open = awake && !accept;
+		if(STATS) { visits += awake ? 1u : 0u; }
 		if(__any_sync(0xffffffffu, accept))
 		{
 			const real m = nmass[curr];
 			if(accept)
 			{
-				node_force(me.x, me.y, me.z, nd, m, ax, ay, az);
-				++inter;
+				node_force_from_test(dx, dy, dz, d2, m, ax, ay, az);
+				if(STATS) { ++inter; }
 				awake = false;
 				resume = skip;
 			}
 		}
 		// descend if any awake lane needs the children; leaves have none (heap_next_up falls back to skip_idx)
-		curr = (__any_sync(0xffffffffu, open) && child < 2 * n) ? child : skip;
+		curr = (__any_sync(0xffffffffu, open) && child < tree_size) ? child : skip;
 	} while(curr != 1);
 	if(live)
 	{
 		store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
 	}
-	if(stats != nullptr && live)
+	if(STATS && live)
 	{
 		atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
 		atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
@@ -637,7 +665,14 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	}
 	else
 	{
-		bh_walk_warp<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		if(stats != nullptr)
+		{
+			bh_walk_warp<true><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		}
+		else
+		{
+			bh_walk_warp<false><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		}
 	}
 	++launches;
 	BH_CU(cudaGetLastError());

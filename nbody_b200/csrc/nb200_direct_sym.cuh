@@ -37,8 +37,11 @@ __device__ __forceinline__ double sym_shfl(double v, int src_lane)
 }
 
 // tile_rc[t] = {row block, column block} of the t-th tile this CTA grid works on
+#ifndef NB200_SYM_MINB
+#define NB200_SYM_MINB 1
+#endif
 template<int I, int J>
-__global__ void __launch_bounds__(NB200_SYM_THREADS, 1)
+__global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
 direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, double* __restrict__ p_row,
 				 double* __restrict__ p_col, int tile_edge)
 {
