@@ -426,8 +426,11 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 }
 
 // one warp per 32 consecutive targets, warp-uniform walk over the union of the lanes' traversals
+#ifndef NB200_BH_WALK_MINB
+#define NB200_BH_WALK_MINB 8	// 8 x 256 threads = all 64 warp slots of an SM (caps the kernel at 32 registers)
+#endif
 template<bool STATS>
-__global__ void __launch_bounds__(256) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+__global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 													 const int* __restrict__ body_n, const int* __restrict__ own_leaf,
 													 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
