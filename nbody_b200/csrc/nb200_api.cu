@@ -111,17 +111,25 @@ void free_lane(nb200_lane& l)
 	l.h_scalar = nullptr;
 }
 
-// Make every lane's `src` hold the packed bodies of all shards.
+// All-gather of one equally sized block per shard inside a per-lane buffer laid out [shard][block]:
+// which == 0: packed source bodies (l.src, 4 reals per body); which == 1: leaf-ordered accelerations of the
+// Barnes-Hut walk (l.bh->acc_all, 3 reals per body).
 // lanes > 1: peer copies between this process's lanes; nranks > 1: NCCL all-gather.
-int gather_sources(nb200_ctx* ctx)
+char* gather_base(nb200_lane& l, int which)
 {
-	const size_t	shard_bytes = ctx->n_shard * sizeof(body4);
+	return which == 0 ? reinterpret_cast<char*>(l.src) : reinterpret_cast<char*>(l.bh->acc_all);
+}
+
+int gather_blocks(nb200_ctx* ctx, int which)
+{
+	const size_t	reals_per_body = which == 0 ? 4 : 3;
+	const size_t	shard_bytes = ctx->n_shard * reals_per_body * sizeof(real);
 	if(ctx->nranks > 1)
 	{
 		nb200_lane&	l = ctx->lanes[0];
-		body4*		mine = l.src + static_cast<size_t>(l.shard) * ctx->n_shard;
-		NC(ctx, ctx->nccl->AllGather(mine, l.src, ctx->n_shard * 4, NB200_NCCL_REAL,
-									 static_cast<ncclComm_t>(ctx->comm), l.stream));
+		char*		base = gather_base(l, which);
+		NC(ctx, ctx->nccl->AllGather(base + static_cast<size_t>(l.shard) * shard_bytes, base, ctx->n_shard * reals_per_body,
+									 NB200_NCCL_REAL, static_cast<ncclComm_t>(ctx->comm), l.stream));
 		return NB200_OK;
 	}
 	if(ctx->lanes.size() > 1)
@@ -138,8 +146,8 @@ int gather_sources(nb200_ctx* ctx)
 			{
 				if(&p == &l) { continue; }
 				CU(ctx, cudaStreamWaitEvent(l.stream, p.ev_packed, 0));
-				size_t off = static_cast<size_t>(p.shard) * ctx->n_shard;
-				CU(ctx, cudaMemcpyPeerAsync(l.src + off, l.dev, p.src + off, p.dev, shard_bytes, l.stream));
+				size_t off = static_cast<size_t>(p.shard) * shard_bytes;
+				CU(ctx, cudaMemcpyPeerAsync(gather_base(l, which) + off, l.dev, gather_base(p, which) + off, p.dev, shard_bytes, l.stream));
 			}
 			CU(ctx, cudaEventRecord(l.ev_gathered, l.stream));
 		}
@@ -181,7 +189,7 @@ int pack_and_gather(nb200_ctx* ctx, const nb200_buf* y)
 												static_cast<size_t>(l.shard) * ctx->n_shard);
 		LAUNCHED(ctx);
 	}
-	int rc = gather_sources(ctx);
+	int rc = gather_blocks(ctx, 0);
 	if(rc != NB200_OK) { return rc; }
 	if(ctx->opt_timing)
 	{
@@ -894,6 +902,22 @@ NB200_API int nb200_fcompute_bh(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f
 		rc = bh_fcompute(ctx, l, lane_ptr(y, li), lane_ptr(f, li), step, launches, err);
 		ctx->launches += static_cast<unsigned long long>(launches);
 		if(rc != NB200_OK) { return fail(ctx, rc, "fcompute_bh: %s", err.c_str()); }
+	}
+	if(ctx->nshards > 1)
+	{
+		// every shard walked its contiguous leaves: gather the leaf-ordered accelerations, then pick own bodies
+		rc = gather_blocks(ctx, 1);
+		if(rc != NB200_OK) { return rc; }
+		for(size_t li = 0; li < ctx->lanes.size(); ++li)
+		{
+			nb200_lane& l = ctx->lanes[li];
+			CU(ctx, cudaSetDevice(l.dev));
+			std::string err;
+			int launches = 0;
+			rc = bh_scatter(ctx, l, lane_ptr(y, li), lane_ptr(f, li), launches, err);
+			ctx->launches += static_cast<unsigned long long>(launches);
+			if(rc != NB200_OK) { return fail(ctx, rc, "fcompute_bh: %s", err.c_str()); }
+		}
 	}
 	return NB200_OK;
 }

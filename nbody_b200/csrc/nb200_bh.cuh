@@ -29,8 +29,12 @@
 //           (nbody_space_heap_stackless.cpp:3-28) -- results are bit-identical to the
 //           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape).
 //
-// The only library primitive is cub::DeviceRadixSort / DeviceSelect (3 presorts per rebuild and
-// the own-leaf compaction when the walk is sharded); everything else is hand-written.
+//   shards  with G shards (lanes or ranks) every shard builds the whole tree, walks the CONTIGUOUS leaves
+//           [g N/G, (g+1) N/G) -- a compact region, so warps stay coherent -- and writes leaf-ordered accelerations;
+//           one all-gather (3N reals) later each shard picks its own bodies through the inverse leaf map. The
+//           reference instead zero-fills f on every device and all-reduces all 6N values (synchronize_sum).
+//
+// The only library primitive is cub::DeviceRadixSort (3 presorts per rebuild); everything else is hand-written.
 #ifndef NB200_BH_CUH
 #define NB200_BH_CUH
 
@@ -67,10 +71,10 @@ struct bh_state
 	unsigned*	blk = nullptr;	// [3][n / PART_BLOCK + 1]
 	void*	cub_tmp = nullptr;
 	size_t	cub_bytes = 0;
-	// sharded walk
-	int*	own_leaf = nullptr;	// leaves whose body belongs to this shard, ascending leaf order
-	unsigned char*	own_flag = nullptr;
-	int*	own_count = nullptr;
+	// sharded walk: shard g walks the contiguous leaves [g*n_shard, (g+1)*n_shard) (a spatially compact set), the
+	// accelerations are gathered in leaf order and each shard picks its own bodies through leaf_pos
+	int*	leaf_pos = nullptr;	// [n] leaf position of every body (inverse of body_n[n..2n))
+	real*	acc_all = nullptr;	// [shards][3][n_shard] accelerations in leaf order
 	bool	have_tree = false;
 	real	built_ratio = 0;
 };
@@ -79,8 +83,8 @@ static void bh_free(bh_state* s)
 {
 	if(s == nullptr) { return; }
 	void* ptrs[] = {s->xyzr, s->nmass, s->bmin, s->bmax, s->body_n, s->keys_in, s->keys_out, s->iota, s->ord[0], s->ord[1],
-					s->ord[2], s->ord_tmp[0], s->ord_tmp[1], s->ord_tmp[2], s->side, s->blk, s->cub_tmp, s->own_leaf,
-					s->own_flag, s->own_count};
+					s->ord[2], s->ord_tmp[0], s->ord_tmp[1], s->ord_tmp[2], s->side, s->blk, s->cub_tmp, s->leaf_pos,
+					s->acc_all};
 	for(void* p : ptrs)
 	{
 		if(p != nullptr) { cudaFree(p); }
@@ -308,13 +312,28 @@ __global__ void __launch_bounds__(256) bh_update_top(node4* xyzr, real* nmass, r
 	}
 }
 
-// ---- sharded walk: which leaves belong to this shard --------------------------------------------------------
-__global__ void __launch_bounds__(256) bh_flag_own(const int* __restrict__ body_n, unsigned char* __restrict__ flag, int n, int lo, int hi)
+// ---- sharded walk helpers -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bh_leaf_positions(const int* __restrict__ body_n, int* __restrict__ leaf_pos, int n)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= n) { return; }
-	int b = body_n[n + i];
-	flag[i] = (b >= lo && b < hi) ? 1 : 0;
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if(k >= n) { return; }
+	leaf_pos[body_n[n + k]] = k;
+}
+
+// f = (v, a) for this shard's bodies from the gathered leaf-ordered accelerations
+__global__ void __launch_bounds__(256) bh_scatter_own(const real* __restrict__ acc_all, const int* __restrict__ leaf_pos,
+													   const real* __restrict__ y, real* __restrict__ f, size_t n_shard, size_t shard_first)
+{
+	size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(i >= n_shard) { return; }
+	const size_t p = static_cast<size_t>(leaf_pos[shard_first + i]);
+	const real*  a = acc_all + (p / n_shard) * 3 * n_shard + (p % n_shard);
+	f[i] = y[3 * n_shard + i];
+	f[n_shard + i] = y[4 * n_shard + i];
+	f[2 * n_shard + i] = y[5 * n_shard + i];
+	f[3 * n_shard + i] = a[0];
+	f[4 * n_shard + i] = a[n_shard];
+	f[5 * n_shard + i] = a[2 * n_shard];
 }
 
 // ---- walk ---------------------------------------------------------------------------------------------------------
@@ -383,13 +402,13 @@ __device__ __forceinline__ void node_force_from_test(real dx, real dy, real dz, 
 
 // one thread per target, independent stackless walks (the reference kernel's shape)
 __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
-													   const int* __restrict__ body_n, const int* __restrict__ own_leaf,
+													   const int* __restrict__ body_n, real* __restrict__ acc_leaf, int leaf_first,
 													   const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													   size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if(t >= n_targets) { return; }
-	const int	leaf = n + (own_leaf != nullptr ? own_leaf[t] : t);
+	const int	leaf = n + leaf_first + t;
 	const int	tree_size = 2 * n;
 	const node4	me = load_node(xyzr, leaf);
 	real		ax = 0, ay = 0, az = 0;
@@ -412,7 +431,16 @@ __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ 
 			curr = heap_next_up(curr, tree_size);
 		}
 	} while(curr != 1);
-	store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
+	if(acc_leaf != nullptr)
+	{
+		acc_leaf[t] = ax;
+		acc_leaf[n_shard + t] = ay;
+		acc_leaf[2 * n_shard + t] = az;
+	}
+	else
+	{
+		store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
+	}
 	if(stats != nullptr)
 	{
 		atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
@@ -431,14 +459,14 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 #endif
 template<bool STATS>
 __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
-													 const int* __restrict__ body_n, const int* __restrict__ own_leaf,
+													 const int* __restrict__ body_n, real* __restrict__ acc_leaf, int leaf_first,
 													 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
 {
 	const int	t = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool	live = t < n_targets;
 	const int	tc = live ? t : n_targets - 1;	// idle lanes shadow the last target and never store
-	const int	leaf = n + (own_leaf != nullptr ? own_leaf[tc] : tc);
+	const int	leaf = n + leaf_first + tc;
 	const int	tree_size = 2 * n;
 	const node4	me = load_node(xyzr, leaf);
 	real		ax = 0, ay = 0, az = 0;
@@ -476,7 +504,16 @@ __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const no
 	} while(curr != 1);
 	if(live)
 	{
-		store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
+		if(acc_leaf != nullptr)
+		{
+			acc_leaf[t] = ax;
+			acc_leaf[n_shard + t] = ay;
+			acc_leaf[2 * n_shard + t] = az;
+		}
+		else
+		{
+			store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf] - shard_first), ax, ay, az);
+		}
 	}
 	if(STATS && live)
 	{
@@ -530,11 +567,7 @@ static int bh_alloc(nb200_ctx* ctx, nb200_lane& l, std::string& err)
 	}
 	if(ok && ctx->nshards > 1)
 	{
-		size_t bytes = 0;
-		cub::DeviceSelect::Flagged(nullptr, bytes, thrust::counting_iterator<int>(0), s->own_flag, s->own_leaf, s->own_count, static_cast<int>(n));
-		s->cub_bytes = std::max(s->cub_bytes, bytes);
-		ok = cudaMalloc(&s->own_leaf, n * sizeof(int)) == cudaSuccess && cudaMalloc(&s->own_flag, n) == cudaSuccess &&
-			 cudaMalloc(&s->own_count, sizeof(int)) == cudaSuccess;
+		ok = cudaMalloc(&s->leaf_pos, n * sizeof(int)) == cudaSuccess && cudaMalloc(&s->acc_all, 3 * n * sizeof(real)) == cudaSuccess;
 	}
 	if(ok && s->cub_bytes > 0) { ok = cudaMalloc(&s->cub_tmp, s->cub_bytes) == cudaSuccess; }
 	if(!ok)
@@ -638,12 +671,8 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 		if(rc != NB200_OK) { return rc; }
 		if(ctx->nshards > 1)
 		{
-			const int lo = static_cast<int>(static_cast<size_t>(l.shard) * ctx->n_shard);
-			bh_flag_own<<<(n + 255) / 256, 256, 0, l.stream>>>(s->body_n, s->own_flag, n, lo, lo + static_cast<int>(ctx->n_shard));
-			size_t bytes = s->cub_bytes;
-			BH_CU(cub::DeviceSelect::Flagged(s->cub_tmp, bytes, thrust::counting_iterator<int>(0), s->own_flag, s->own_leaf,
-											 s->own_count, n, l.stream));
-			launches += 1;
+			bh_leaf_positions<<<(n + 255) / 256, 256, 0, l.stream>>>(s->body_n, s->leaf_pos, n);
+			++launches;
 		}
 		s->have_tree = true;
 	}
@@ -658,24 +687,23 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 		stats = l.d_scalar;
 	}
 	const int	n_targets = static_cast<int>(ctx->n_shard);
-	const int*	own = ctx->nshards > 1 ? s->own_leaf : nullptr;
 	const int	shard_first = static_cast<int>(static_cast<size_t>(l.shard) * ctx->n_shard);
+	// one shard: results go straight to f by body index; several: contiguous leaves -> leaf-ordered block of acc_all
+	real*		acc_leaf = ctx->nshards > 1 ? s->acc_all + static_cast<size_t>(l.shard) * 3 * ctx->n_shard : nullptr;
+	const int	leaf_first = ctx->nshards > 1 ? shard_first : 0;
 	const int	block = (ctx->opt_walk_threads == 64 || ctx->opt_walk_threads == 256) ? static_cast<int>(ctx->opt_walk_threads) : 128;
 	const unsigned grid = static_cast<unsigned>((n_targets + block - 1) / block);
 	if(ctx->opt_walk_block == 1)
 	{
-		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, leaf_first, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+	}
+	else if(stats != nullptr)
+	{
+		bh_walk_warp<true><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, leaf_first, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}
 	else
 	{
-		if(stats != nullptr)
-		{
-			bh_walk_warp<true><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
-		}
-		else
-		{
-			bh_walk_warp<false><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, own, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
-		}
+		bh_walk_warp<false><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, leaf_first, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}
 	++launches;
 	BH_CU(cudaGetLastError());
@@ -684,6 +712,18 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 		BH_CU(cudaEventRecord(l.ev_t[3], l.stream));
 		BH_CU(cudaEventRecord(l.ev_t[4], l.stream));
 	}
+	return NB200_OK;
+}
+
+// second half of a sharded fcompute, after acc_all has been gathered across shards
+static int bh_scatter(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, int& launches, std::string& err)
+{
+	bh_state* s = l.bh;
+	bh_scatter_own<<<static_cast<unsigned>((ctx->n_shard + 255) / 256), 256, 0, l.stream>>>(
+		s->acc_all, s->leaf_pos, y, f, ctx->n_shard, static_cast<size_t>(l.shard) * ctx->n_shard);
+	++launches;
+	BH_CU(cudaGetLastError());
+	if(ctx->opt_timing) { BH_CU(cudaEventRecord(l.ev_t[4], l.stream)); }
 	return NB200_OK;
 }
 
