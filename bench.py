@@ -335,7 +335,12 @@ def run_nb200(args):
                         "frac_issued": (pairs_per_launch * issued / (force_ms * 1e-3)) / fma_peak if fma_peak else None,
                         "peak_source": "nb200_probe_fma_peak (FMA chain kernel of this precision, this run); MEASURED_PEAKS.json has no "
                                        "FP64/FP32 vector entry; nominal 148 SM x 64 (FP64) / 128 (FP32) FMA/clk x 1.965 GHz = 37.2 / 74.4 TFLOP/s",
-                        "traffic_note": "ncu --set full (profiles/r1_ncu_direct_pairs.csv): 48 MB DRAM read + 60 MB written per launch at N=1M"}
+                        "traffic_note": "ordered-pair kernel at N=1M (profiles/r1_ncu_direct_pairs.csv): 48 MB DRAM read + 60 MB written per launch"}
+            if sym_edge == 8192 and n == N_DIRECT and world == 1:
+                # one ncu --set full capture of this exact launch (profiles/r1_ncu_direct_sym_tiles_n1m.csv):
+                # dram__bytes_read.sum 0.314 GB + dram__bytes_write.sum 3.214 GB (the tile partials) per launch
+                roofline["traffic"] = 3.528e9
+                roofline["traffic_source"] = "profiles/r1_ncu_direct_sym_tiles_n1m.csv (bytes per launch; compute-bound kernel)"
             e2e_obj = None
             if e2e:
                 e2e_obj = {"value": pairs * args.steps / e2e[0], "unit": unit, "h2d_bytes_per_step": e2e[1],
@@ -359,6 +364,11 @@ def run_nb200(args):
                         "note": "algorithmic bytes count every per-target node visit; the warp-coherent walk loads each node once per warp "
                                 "and the upper tree stays in L1/L2, so the fraction can exceed 1 (SURVEY 8d says so); see profiles/ for DRAM bytes",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm else "fallback 6.65 TB/s (B200_PROFILING.md)"}
+            if n == N_BH and world == 1 and args.ratio == 10.0 and precision == "f64":
+                # one ncu --set full capture of this exact launch (profiles/r1_ncu_bh_walk_n4m.csv):
+                # dram__bytes_read.sum 3.035 GB + dram__bytes_write.sum 0.804 GB per launch; L2 hit 98.5 %, L1 hit 38 %
+                roofline["traffic"] = 3.840e9
+                roofline["traffic_source"] = "profiles/r1_ncu_bh_walk_n4m.csv (bytes per launch)"
             e2e_obj = None
             if e2e:
                 e2e_obj = {"value": e2e[0] * 1e3 / args.steps, "unit": unit, "h2d_bytes_per_step": e2e[1],
