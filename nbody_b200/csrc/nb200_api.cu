@@ -666,7 +666,6 @@ NB200_API int nb200_fill(nb200_ctx* ctx, nb200_buf* a, nb200_real value)
 
 // ---- direct all-pairs --------------------------------------------------------------
 namespace {
-#if NB200_PRECISION == 2
 // Tile edge of the symmetric path for this problem, 0 = use the plain kernel.
 int sym_tile_edge(const nb200_ctx* ctx)
 {
@@ -773,7 +772,6 @@ int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
 	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }
 	return NB200_OK;
 }
-#endif
 }  // namespace
 
 NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f)
@@ -783,13 +781,11 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_direct: y and f must differ"); }
 	rc = pack_and_gather(ctx, y);
 	if(rc != NB200_OK) { return rc; }
-#if NB200_PRECISION == 2
 	if(const int edge = sym_tile_edge(ctx))
 	{
 		ctx->last_direct_path = edge;
 		return sym_fcompute(ctx, y, f, edge);
 	}
-#endif
 	ctx->last_direct_path = 0;
 
 	const int	n_tiles = static_cast<int>(ctx->n_pad / NB200_DIRECT_TILE);

@@ -97,7 +97,8 @@ struct nb200_ctx
 	long long	opt_timing = 1;
 	long long	opt_direct_sym = -1;	// -1 auto, 0 off, 1 force
 	long long	opt_sym_tile = 0;		// tile edge override (multiple of 256)
-	long long	opt_sym_shape = 1;		// bodies per lane (row x column): 0: 8 x 1, 1: 4 x 2 (fastest measured), 2: 8 x 2, 3: 4 x 4
+	// bodies per lane (row x column): 0: 8 x 1, 1: 4 x 2, 2: 8 x 2, 3: 4 x 4; fastest measured: 4 x 2 (FP64), 8 x 2 (FP32)
+	long long	opt_sym_shape = sizeof(real) == 8 ? 1 : 2;
 };
 
 struct nb200_buf

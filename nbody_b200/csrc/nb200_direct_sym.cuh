@@ -1,4 +1,4 @@
-// nb200 -- symmetric (Newton's third law) all-pairs tiles for large N, FP64.
+// nb200 -- symmetric (Newton's third law) all-pairs tiles for N >= 32,768 (FP64 and FP32 builds).
 //
 // The plain kernel (nb200_direct.cuh) evaluates every ORDERED pair: 17 FP64-pipe instructions per interaction.
 // Here every UNORDERED pair is evaluated once and applied to both bodies (a_i += m_j c d, a_j -= m_i c d):
@@ -24,17 +24,64 @@
 
 #include "nb200_common.cuh"
 
-#if NB200_PRECISION == 2
-
 #define NB200_SYM_WARPS 8
 #define NB200_SYM_THREADS (32 * NB200_SYM_WARPS)
 
+#if NB200_PRECISION == 2
 __device__ __forceinline__ double sym_shfl(double v, int src_lane)
 {
 	int lo = __shfl_sync(0xffffffffu, __double2loint(v), src_lane);
 	int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src_lane);
 	return __hiloint2double(hi, lo);
 }
+// one unordered pair: d = column - row; both accumulator sets updated (21 FP64-pipe instructions)
+__device__ __forceinline__ void sym_pair(double dx, double dy, double dz, double m_row, double m_col,
+										 double& ax, double& ay, double& az, double& bx, double& by, double& bz)
+{
+	double	r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+	long long		bits = __double_as_longlong(r2);
+	const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8, exact clamp on the integer pipe
+	bits = bits < min_bits ? min_bits : bits;
+	r2 = __longlong_as_double(bits);
+	double	y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+	double	h = r2 * y0;
+	double	e = fma(-h, y0, 1.0);
+	double	pp = fma(e, 0.375, 0.5);
+	double	qq = y0 * e;
+	double	y = fma(qq, pp, y0);
+	double	y3 = (y * y) * y;
+	double	ca = m_col * y3;
+	double	cb = m_row * y3;
+	ax = fma(dx, ca, ax);
+	ay = fma(dy, ca, ay);
+	az = fma(dz, ca, az);
+	bx = fma(-dx, cb, bx);
+	by = fma(-dy, cb, by);
+	bz = fma(-dz, cb, bz);
+}
+#else
+__device__ __forceinline__ float sym_shfl(float v, int src_lane)
+{
+	return __shfl_sync(0xffffffffu, v, src_lane);
+}
+// FP32: 16 FP32-pipe instructions + MUFU.RSQ + FMNMX per unordered pair
+__device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_row, float m_col,
+										 float& ax, float& ay, float& az, float& bx, float& by, float& bz)
+{
+	float	r2 = fmaxf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), NB200_MIN_DISTANCE);
+	float	y = rsqrtf(r2);
+	float	y3 = (y * y) * y;
+	float	ca = m_col * y3;
+	float	cb = m_row * y3;
+	ax = fmaf(dx, ca, ax);
+	ay = fmaf(dy, ca, ay);
+	az = fmaf(dz, ca, az);
+	bx = fmaf(-dx, cb, bx);
+	by = fmaf(-dy, cb, by);
+	bz = fmaf(-dz, cb, bz);
+}
+#endif
 
 // tile_rc[t] = {row block, column block} of the t-th tile this CTA grid works on
 #ifndef NB200_SYM_MINB
@@ -42,10 +89,10 @@ __device__ __forceinline__ double sym_shfl(double v, int src_lane)
 #endif
 template<int I, int J>
 __global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
-direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, double* __restrict__ p_row,
-				 double* __restrict__ p_col, int tile_edge)
+direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, real* __restrict__ p_row,
+				 real* __restrict__ p_col, int tile_edge)
 {
-	extern __shared__ double colacc[];	// [3][tile_edge]
+	extern __shared__ real colacc[];	// [3][tile_edge]
 	const int	T = tile_edge;
 	const int	lane = threadIdx.x & 31;
 	const int	warp = threadIdx.x >> 5;
@@ -53,8 +100,8 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 	const bool	diagonal = rc.x == rc.y;
 	const body4* __restrict__ rows = src + static_cast<size_t>(rc.x) * T;
 	const body4* __restrict__ cols = src + static_cast<size_t>(rc.y) * T;
-	double*		out_row = p_row + static_cast<size_t>(blockIdx.x) * 3 * T;
-	double*		out_col = p_col + static_cast<size_t>(blockIdx.x) * 3 * T;
+	real*		out_row = p_row + static_cast<size_t>(blockIdx.x) * 3 * T;
+	real*		out_col = p_col + static_cast<size_t>(blockIdx.x) * 3 * T;
 	const int	n_ablk = T / (32 * I);	// row blocks of the tile, dealt to the warps round-robin
 	const int	n_bblk = T / (32 * J);	// column blocks of the tile
 	const int	from = (lane + 31) & 31;	// the column group arrives from lane - 1
@@ -70,7 +117,7 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 		// every warp runs every phase (the phase barrier is block-wide); warps without a row block just keep step
 		const int	ablk = a0 + warp;
 		const bool	active = ablk < n_ablk;
-		double xa[I], ya[I], za[I], ma[I], ax[I], ay[I], az[I];
+		real xa[I], ya[I], za[I], ma[I], ax[I], ay[I], az[I];
 #pragma unroll
 		for(int k = 0; k < I; ++k)
 		{
@@ -90,7 +137,7 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 		{
 			if(active)
 			{
-			double xb[J], yb[J], zb[J], mb[J], bx[J], by[J], bz[J];
+			real xb[J], yb[J], zb[J], mb[J], bx[J], by[J], bz[J];
 #pragma unroll
 			for(int q = 0; q < J; ++q)
 			{
@@ -117,30 +164,8 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 #pragma unroll
 					for(int k = 0; k < I; ++k)
 					{
-						double	dx = xb[q] - xa[k];
-						double	dy = yb[q] - ya[k];
-						double	dz = zb[q] - za[k];
-						double	r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-						long long		bits = __double_as_longlong(r2);
-						const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8, exact clamp on the integer pipe
-						bits = bits < min_bits ? min_bits : bits;
-						r2 = __longlong_as_double(bits);
-						double	y0;
-						asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
-						double	h = r2 * y0;
-						double	e = fma(-h, y0, 1.0);
-						double	pp = fma(e, 0.375, 0.5);
-						double	qq = y0 * e;
-						double	y = fma(qq, pp, y0);
-						double	y3 = (y * y) * y;
-						double	ca = mb[q] * y3;
-						double	cb = ma[k] * y3;
-						ax[k] = fma(dx, ca, ax[k]);
-						ay[k] = fma(dy, ca, ay[k]);
-						az[k] = fma(dz, ca, az[k]);
-						bx[q] = fma(-dx, cb, bx[q]);
-						by[q] = fma(-dy, cb, by[q]);
-						bz[q] = fma(-dz, cb, bz[q]);
+						sym_pair(xb[q] - xa[k], yb[q] - ya[k], zb[q] - za[k], ma[k], mb[q],
+								 ax[k], ay[k], az[k], bx[q], by[q], bz[q]);
 					}
 				}
 #pragma unroll
@@ -193,8 +218,8 @@ __host__ __device__ __forceinline__ long long sym_tile_id(int r, int c, int S)
 // acc[comp][body] = sum of the partials of every tile of THIS rank that touches the body's block, in a fixed order:
 // column sums of tiles (a, blk), a < blk, ascending a; then row sums of tiles (blk, c), c >= blk, ascending c.
 // out layout: [shard][comp][n_shard] over all N bodies (the send buffer of the reduce-scatter; [3][N] for one shard).
-__global__ void __launch_bounds__(256) direct_sym_reduce(const double* __restrict__ p_row, const double* __restrict__ p_col,
-														 double* __restrict__ out, size_t n_bodies, size_t n_shard,
+__global__ void __launch_bounds__(256) direct_sym_reduce(const real* __restrict__ p_row, const real* __restrict__ p_col,
+														 real* __restrict__ out, size_t n_bodies, size_t n_shard,
 														 int tile_edge, int S, int rank, int nranks)
 {
 	const size_t body = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -202,7 +227,7 @@ __global__ void __launch_bounds__(256) direct_sym_reduce(const double* __restric
 	{
 		return;
 	}
-	double			acc[3] = {0, 0, 0};
+	real			acc[3] = {0, 0, 0};
 	{
 		const int		T = tile_edge;
 		const int		blk = static_cast<int>(body / T);
@@ -212,7 +237,7 @@ __global__ void __launch_bounds__(256) direct_sym_reduce(const double* __restric
 			const long long id = sym_tile_id(a, blk, S);
 			if(id % nranks == rank)
 			{
-				const double* p = p_col + static_cast<size_t>(id / nranks) * 3 * T + off;
+				const real* p = p_col + static_cast<size_t>(id / nranks) * 3 * T + off;
 				acc[0] += p[0]; acc[1] += p[T]; acc[2] += p[2 * T];
 			}
 		}
@@ -221,21 +246,21 @@ __global__ void __launch_bounds__(256) direct_sym_reduce(const double* __restric
 			const long long id = sym_tile_id(blk, c, S);
 			if(id % nranks == rank)
 			{
-				const double* p = p_row + static_cast<size_t>(id / nranks) * 3 * T + off;
+				const real* p = p_row + static_cast<size_t>(id / nranks) * 3 * T + off;
 				acc[0] += p[0]; acc[1] += p[T]; acc[2] += p[2 * T];
 			}
 		}
 	}
 	const size_t shard = body / n_shard, local = body % n_shard;
-	double* o = out + shard * 3 * n_shard + local;
+	real* o = out + shard * 3 * n_shard + local;
 	o[0] = acc[0];
 	o[n_shard] = acc[1];
 	o[2 * n_shard] = acc[2];
 }
 
 // f = (v, a) for the local shard from an acceleration block laid out [3][n_shard]
-__global__ void __launch_bounds__(256) direct_sym_finish(const double* __restrict__ acc, const double* __restrict__ y,
-														 double* __restrict__ f, size_t n_shard)
+__global__ void __launch_bounds__(256) direct_sym_finish(const real* __restrict__ acc, const real* __restrict__ y,
+														 real* __restrict__ f, size_t n_shard)
 {
 	const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if(e >= 3 * n_shard)
@@ -246,5 +271,4 @@ __global__ void __launch_bounds__(256) direct_sym_finish(const double* __restric
 	f[3 * n_shard + e] = acc[e];
 }
 
-#endif // NB200_PRECISION == 2
 #endif // NB200_DIRECT_SYM_CUH

@@ -203,3 +203,16 @@ def test_direct_symmetric_is_the_large_n_default(oracle64):
     force = (f[3:] * m[None, :]).sum(axis=1)
     scale = np.abs(f[3:] * m[None, :]).sum(axis=1)
     assert np.all(np.abs(force) <= 1e-11 * scale)
+
+
+@pytest.mark.parametrize("n,tile", [(4096, 1024), (5000, 512)])
+def test_direct_symmetric_tiles_fp32(oracle32, oracle64, n, tile):
+    rng = np.random.RandomState(n)
+    y = rng.uniform(-50, 50, 6 * n).astype(np.float32)
+    m = rng.uniform(0.1, 2.0, n).astype(np.float32)
+    f = run_direct(y, m, precision="f32", options=(("direct_symmetric", 1), ("direct_sym_tile", tile)))
+    ref32 = oracle32.fcompute_openmp(y, m)
+    truth = oracle64.fcompute_openmp(y.astype(np.float64), m.astype(np.float64))
+    assert np.array_equal(f[:3 * n], y[3 * n:])
+    assert rel_err_per_body(f, ref32, n) <= TOL32
+    assert rel_err_per_body(f, truth, n) <= max(2 * rel_err_per_body(ref32, truth, n), 2e-6)
