@@ -37,7 +37,8 @@ os.environ.setdefault("NBREF_QUIET", "1")
 
 N_DIRECT = 1 << 20
 N_BH = 1 << 22
-N_CPU_SAMPLE = 32768
+N_CPU_SAMPLE = 131072        # cpu_baseline sample: 1.7e10 pairs, ~5-20 s of CPU work per fcompute on 16-64 cores
+N_CPU_STEP = 65536           # --impl reference: bodies per timed step (4.3e9 pairs, ~1 s on 16 cores)
 # FMA-pipe instruction slots per pair -- FP64: 18 (the kernel issues 17); FP32: 13 (+1 MUFU on XU)
 SLOTS_PER_PAIR = {"f64": 18, "f32": 13}
 ISSUED_PER_PAIR = {"f64": 17, "f32": 13}
@@ -128,12 +129,12 @@ class ClockSampler:
 
 
 # ---- CPU baseline / reference arm -----------------------------------------------------
-def cpu_reference_rate(workload, precision, ratio, reps=1):
+def cpu_reference_rate(workload, precision, ratio, reps=1, n_direct=None):
     """Reference CPU engine on the host cores, bounded sample. Returns dict(value, unit, cores, kind, sample)."""
     from oracle import refharness as R
     cores = os.cpu_count() or 1
     if workload == "direct":
-        n = N_CPU_SAMPLE
+        n = n_direct or N_CPU_SAMPLE
         y, m, _ = make_inputs(n, precision)
         if R.available(precision):
             lib = R.load(precision)
@@ -154,9 +155,9 @@ def cpu_reference_rate(workload, precision, ratio, reps=1):
             o.fcompute_openmp(y, m)
             sec = time.perf_counter() - t0
             kind, what = "port", "oracle/nbody_oracle.c orc_fcompute_openmp"
-        return {"value": n * n / sec, "unit": "pair interactions/s", "cores": cores, "kind": kind,
-                "sample": "%s, one fcompute at N=%d (%.1f s); rate is N-independent, N=1M extrapolates to %.0f s"
-                          % (what, n, sec, (N_DIRECT ** 2) / (n * n / sec))}
+        return {"value": n * n / sec, "unit": "pair interactions/s", "cores": cores, "kind": kind, "bodies": n, "seconds": sec,
+                "sample": "%s, best of %d fcompute at N=%d after one warm-up (%.1f s each); rate is N-independent, "
+                          "N=1M extrapolates to %.0f s" % (what, max(1, reps), n, sec, (N_DIRECT ** 2) / (n * n / sec))}
     n = 1 << 18
     y, m, _ = make_inputs(n, precision)
     if R.available(precision):
@@ -188,16 +189,16 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    total = args.steps + args.warmup
     t0 = time.perf_counter()
-    res = cpu_reference_rate(args.workload, args.precision, args.ratio, reps=max(1, min(total - 1, 2)))
+    # W warm-up + K timed steps, each step one reference fcompute on a bounded sample (N_CPU_STEP bodies)
+    res = cpu_reference_rate(args.workload, args.precision, args.ratio, reps=max(1, args.steps), n_direct=N_CPU_STEP)
     wall = time.perf_counter() - t0
     direct = args.workload == "direct"
     line = {
         "impl": "reference",
         "metric": "pair interactions/s (FP64 direct all-pairs fcompute)" if direct else "Barnes-Hut fcompute ms/step",
         "value": res["value"], "unit": res["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": (N_CPU_SAMPLE ** 2 / res["value"] * 1e3) if direct else res["value"],
+        "ms_per_step": (res["seconds"] * 1e3) if direct else res["value"],
         "higher_is_better": direct, "scaling": "strong", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": ("direct all-pairs fcompute, reference CPU engine on a bounded sample of the N=1M workload"
