@@ -671,6 +671,7 @@ int sym_tile_edge(const nb200_ctx* ctx)
 {
 	if(ctx->lanes.size() != 1 || ctx->opt_direct_sym == 0) { return 0; }
 	if(ctx->opt_direct_sym < 0 && ctx->n < 32768) { return 0; }	// too few tiles to fill 148 SMs
+	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(3) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }	// partials > ~30 GB per rank
 	// automatic edge: ~N/128 (>= 8000 equal tiles), at most 8192 (192 KB of column sums; scratch 24 N^2 / T bytes)
 	long long edge = ctx->opt_sym_tile;
 	if(edge <= 0)
@@ -784,7 +785,10 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	if(const int edge = sym_tile_edge(ctx))
 	{
 		ctx->last_direct_path = edge;
-		return sym_fcompute(ctx, y, f, edge);
+		rc = sym_fcompute(ctx, y, f, edge);
+		if(rc != NB200_ERR_ALLOC) { return rc; }
+		// the tile partials (24 N^2 / T bytes) did not fit next to the caller's buffers: ordered-pair kernel from now on
+		ctx->opt_direct_sym = 0;
 	}
 	ctx->last_direct_path = 0;
 
