@@ -103,6 +103,9 @@ void free_lane(nb200_lane& l)
 	l.sym_edge = 0;
 	l.partial_elems = 0;
 	if(l.d_scalar) { cudaFree(l.d_scalar); }
+	if(l.read_scratch) { cudaFree(l.read_scratch); }
+	l.read_scratch = nullptr;
+	l.read_scratch_bytes = 0;
 	if(l.h_scalar) { cudaFreeHost(l.h_scalar); }
 	l.mass = nullptr;
 	l.src = nullptr;
@@ -596,30 +599,27 @@ NB200_API int nb200_read(nb200_ctx* ctx, void* host, const nb200_buf* src)
 	{
 		// All ranks call read at the same point: gather the shards, then un-interleave on the host.
 		nb200_lane&	l = ctx->lanes[0];
-		real*		all = nullptr;
 		CU(ctx, cudaSetDevice(l.dev));
-		if(cudaMalloc(&all, src->bytes) != cudaSuccess)
+		if(l.read_scratch_bytes < src->bytes)
 		{
-			cudaGetLastError();
-			return fail(ctx, NB200_ERR_ALLOC, "read: gather scratch allocation failed");
+			if(l.read_scratch) { cudaFree(l.read_scratch); l.read_scratch = nullptr; l.read_scratch_bytes = 0; }
+			if(cudaMalloc(&l.read_scratch, src->bytes) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return fail(ctx, NB200_ERR_ALLOC, "read: gather scratch allocation failed");
+			}
+			l.read_scratch_bytes = src->bytes;
 		}
-		ncclResult_t r = ctx->nccl->AllGather(src->dptr[0], all, src->lane_elems, NB200_NCCL_REAL,
-											  static_cast<ncclComm_t>(ctx->comm), l.stream);
-		if(r != ncclSuccess)
-		{
-			cudaFree(all);
-			return fail(ctx, NB200_ERR_NCCL, "read: ncclAllGather: %s", ctx->nccl->GetErrorString(r));
-		}
-		cudaError_t ce = cudaSuccess;
-		for(int g = 0; g < ctx->nshards && ce == cudaSuccess; ++g)
+		real* all = l.read_scratch;
+		NC(ctx, ctx->nccl->AllGather(src->dptr[0], all, src->lane_elems, NB200_NCCL_REAL,
+									 static_cast<ncclComm_t>(ctx->comm), l.stream));
+		for(int g = 0; g < ctx->nshards; ++g)
 		{
 			char* dst = static_cast<char*>(host) + static_cast<size_t>(g) * ctx->n_shard * sizeof(real);
-			ce = cudaMemcpy2DAsync(dst, ctx->n * sizeof(real), all + static_cast<size_t>(g) * src->lane_elems,
-								   ctx->n_shard * sizeof(real), ctx->n_shard * sizeof(real), 6, cudaMemcpyDeviceToHost, l.stream);
+			CU(ctx, cudaMemcpy2DAsync(dst, ctx->n * sizeof(real), all + static_cast<size_t>(g) * src->lane_elems,
+									  ctx->n_shard * sizeof(real), ctx->n_shard * sizeof(real), 6, cudaMemcpyDeviceToHost, l.stream));
 		}
-		if(ce == cudaSuccess) { ce = cudaStreamSynchronize(l.stream); }
-		cudaFree(all);
-		if(ce != cudaSuccess) { return fail(ctx, NB200_ERR_CUDA, "read: %s", cudaGetErrorString(ce)); }
+		CU(ctx, cudaStreamSynchronize(l.stream));
 		return NB200_OK;
 	}
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)

@@ -63,6 +63,8 @@ struct nb200_lane
 	unsigned long long*	d_scalar = nullptr;	// device scratch: maxabs bits, walk counters (4 x u64)
 	unsigned long long*	h_scalar = nullptr;	// pinned mirror
 	bh_state*		bh = nullptr;
+	real*			read_scratch = nullptr;	// [shards][6][n_shard] staging of a multi-rank read_buffer
+	size_t			read_scratch_bytes = 0;
 };
 
 struct nccl_api;
