@@ -573,6 +573,41 @@ void orc_fcompute_bh(size_t n, const orc_real* y, const orc_real* mass,
 	if(inter_out) { *inter_out = inter; }
 }
 
+void orc_bh_subset(size_t n, const orc_real* xyzr, const orc_real* node_mass, const size_t* leaves, size_t nt, orc_real* acc)
+{
+	const size_t tree_size = 2 * n;
+	#pragma omp parallel for schedule(dynamic, 1)
+	for(size_t t = 0; t < nt; ++t)
+	{
+		size_t		leaf = n + leaves[t];
+		v3			v1 = {xyzr[4 * leaf], xyzr[4 * leaf + 1], xyzr[4 * leaf + 2]};
+		orc_real	mass1 = node_mass[leaf];
+		v3			total = {0, 0, 0};
+		size_t		curr = 1;
+		do
+		{
+			v3			cm = {xyzr[4 * curr], xyzr[4 * curr + 1], xyzr[4 * curr + 2]};
+			orc_real	dx = v1.x - cm.x, dy = v1.y - cm.y, dz = v1.z - cm.z;
+			orc_real	d2 = dx * dx + dy * dy + dz * dz;
+			if(d2 > xyzr[4 * curr + 3])
+			{
+				v3 fo = force(v1, cm, mass1, node_mass[curr]);
+				total.x += fo.x;
+				total.y += fo.y;
+				total.z += fo.z;
+				curr = orc_heap_skip(curr);
+			}
+			else
+			{
+				curr = orc_heap_next_up(curr, tree_size);
+			}
+		} while(curr != 1);
+		acc[t] = total.x / mass1;
+		acc[nt + t] = total.y / mass1;
+		acc[2 * nt + t] = total.z / mass1;
+	}
+}
+
 /* ---- solvers ---------------------------------------------------------------- */
 void orc_run_euler(size_t n, orc_real* y, const orc_real* mass, orc_real dt, orc_real max_time)
 {

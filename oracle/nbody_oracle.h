@@ -78,6 +78,10 @@ void orc_fcompute_bh(size_t n, const orc_real* y, const orc_real* mass,
 					 const orc_real* xyzr, const orc_real* node_mass, const long long* body_n,
 					 int stackless, orc_real* f, unsigned long long* visits, unsigned long long* interactions);
 
+/* Stackless walk for a subset of leaves (leaf = heap index - n); acc is 3 x nt accelerations (already divided by the
+ * target's mass, like update_f). Lets the N = 4M configuration be spot-checked in seconds. */
+void orc_bh_subset(size_t n, const orc_real* xyzr, const orc_real* node_mass, const size_t* leaves, size_t nt, orc_real* acc);
+
 /* ---- two solvers restated to pin the oracle on the golden files ------------
  * nbody_solver_euler.cpp, nbody_solver_rk4.cpp:19-48 driven like
  * nbody_solver::run (nbody_solver.cpp:73-76): while(t < max_time) advise(dt). */

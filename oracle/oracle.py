@@ -59,6 +59,7 @@ def load(precision="f64"):
     sig("orc_heap_build", i32, sz, vp, vp, real, vp, vp, vp, vp, vp)
     sig("orc_heap_rebuild", None, sz, vp, real, vp, vp, vp, vp, vp)
     sig("orc_fcompute_bh", None, sz, vp, vp, vp, vp, vp, i32, vp, vp, vp)
+    sig("orc_bh_subset", None, sz, vp, vp, vp, sz, vp)
     sig("orc_run_euler", None, sz, vp, vp, real, real)
     sig("orc_run_rk4", None, sz, vp, vp, real, real)
     sig("orc_statistics", None, sz, vp, vp, i32, vp)
@@ -180,6 +181,13 @@ class Oracle:
         self.lib.orc_fcompute_bh(mass.size, _p(y), _p(mass), _p(tree["xyzr"]), _p(tree["mass"]), _p(tree["body_n"]),
                                  1 if stackless else 0, _p(f), C.byref(v), C.byref(k))
         return f, v.value, k.value
+
+    def bh_subset(self, tree, leaves):
+        """Accelerations (3 x nt) of the targets at the given leaf positions, walking `tree` like simple_bh."""
+        t = np.ascontiguousarray(leaves, dtype=np.uint64)
+        acc = np.empty(3 * t.size, dtype=self.dtype)
+        self.lib.orc_bh_subset(tree["n"], _p(tree["xyzr"]), _p(tree["mass"]), _p(t), t.size, _p(acc))
+        return acc.reshape(3, t.size)
 
     # solvers / statistics
     def run(self, solver, y, mass, dt, max_time):

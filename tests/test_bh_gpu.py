@@ -166,3 +166,21 @@ def test_bh_n1m_tree_equals_oracle_and_walk_ratio1(oracle64):
     want, visits, inter = oracle64.fcompute_bh(y, m, t)
     assert st == (visits, inter)
     assert rel_err_per_body(f, want, n) <= TOL
+
+
+def test_bh_c4_n4m_ratio10_sampled(oracle64):
+    """BASELINE config C4 (N = 4,194,304, ratio 10): leaf order identical to the CPU build; accelerations of 384
+    sampled targets (incl. both central bodies' leaves) vs the oracle's stackless walk of the same tree."""
+    n = 1 << 22
+    y, m = universe(n)
+    (f,), (xyzr, mass, body), _ = run_bh(y, m, 10.0)
+    t = oracle64.heap_build(y, m, 10.0)
+    assert np.array_equal(body[n:], t["body_n"][n:].astype(np.int32))
+    assert np.allclose(xyzr[1:, :3], t["xyzr"][1:, :3], rtol=1e-12, atol=1e-12)
+    leaf_of = np.empty(n, dtype=np.int64)
+    leaf_of[t["body_n"][n:]] = np.arange(n)
+    bodies = np.unique(np.concatenate([[0, n // 2, n - 1], np.random.RandomState(4).randint(0, n, 381)]))
+    want = oracle64.bh_subset(t, leaf_of[bodies])
+    got = f.reshape(6, n)[3:, bodies]
+    assert rel_err_per_body(got, want, bodies.size) <= TOL
+    assert np.array_equal(f[:3 * n], y[3 * n:])
