@@ -322,8 +322,8 @@ def run_nb200(args):
             kernel = "direct_pairs"
             if sym_edge:
                 # symmetric tiles: 21 FP64-pipe (16 FP32-pipe) instructions per UNORDERED pair = 10.5 (8) per interaction
-                issued = 10.5 if precision == "f64" else 8
-                kernel = "direct_sym_tiles<%s> (tile edge %d)" % ("4,2" if precision == "f64" else "8,2", sym_edge)
+                issued = 10.5 if precision == "f64" else 4   # FP32: 16 packed two-wide instructions per 2 unordered pairs
+                kernel = "%s (tile edge %d)" % ("direct_sym_tiles<4,2>" if precision == "f64" else "direct_sym_tiles_f32x2<8>", sym_edge)
             achieved = pairs_per_launch * 2 * slots / (force_ms * 1e-3) / 1e12
             peak = fma_peak * 2 / 1e12
             roofline = {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe",

@@ -72,6 +72,13 @@ bool valid(const nb200_ctx* ctx, const nb200_buf* b)
 	return ctx != nullptr && b != nullptr && ctx->live.count(b) != 0;
 }
 
+// Same logical size AND same per-lane layout (a state-sized buffer created before nb200_set_bodies is replicated,
+// one created after it is body-sharded: mixing the two would run past the shorter shard)
+bool same_shape(const nb200_buf* a, const nb200_buf* b)
+{
+	return a->bytes == b->bytes && a->lane_elems == b->lane_elems && a->sharded == b->sharded;
+}
+
 unsigned ew_grid(const nb200_lane& lane, size_t count)
 {
 	size_t	nvec = (count + NB200_VEC - 1) / NB200_VEC;
@@ -638,7 +645,7 @@ NB200_API int nb200_copy(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b)
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "copy: a is not a buffer of this context"); }
 	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "copy: b is not a buffer of this context"); }
-	if(a->bytes != b->bytes) { return fail(ctx, NB200_ERR_ARG, "copy: size does not match"); }
+	if(!same_shape(a, b)) { return fail(ctx, NB200_ERR_ARG, "copy: size does not match"); }
 	if(a == b || a->lane_bytes == 0) { return NB200_OK; }
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
@@ -729,6 +736,22 @@ int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
 	const size_t smem = 3 * static_cast<size_t>(T) * sizeof(real);
 	if(mine > 0)
 	{
+#if NB200_PRECISION == 1
+		// FP32: packed f32x2 kernels for the two-column shapes (4: 8 x 2 packed, 5: 4 x 2 packed)
+		if(ctx->opt_sym_shape == 4)
+		{
+			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles_f32x2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			direct_sym_tiles_f32x2<8><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
+				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		}
+		else if(ctx->opt_sym_shape == 5)
+		{
+			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles_f32x2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			direct_sym_tiles_f32x2<4><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
+				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		}
+		else
+#endif
 		if(ctx->opt_sym_shape == 2)
 		{
 			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -961,7 +984,7 @@ NB200_API int nb200_fmadd_inplace(nb200_ctx* ctx, nb200_buf* a, const nb200_buf*
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: a is not a buffer of this context"); }
 	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: b is not a buffer of this context"); }
-	if(a->bytes != b->bytes) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: size does not match"); }
+	if(!same_shape(a, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: size does not match"); }
 	if(a->lane_elems == 0) { return NB200_OK; }
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
@@ -979,7 +1002,7 @@ NB200_API int nb200_fmadd(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, cons
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmadd: a is not a buffer of this context"); }
 	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd: b is not a buffer of this context"); }
 	if(!valid(ctx, c)) { return fail(ctx, NB200_ERR_ARG, "fmadd: c is not a buffer of this context"); }
-	if(a->bytes != b->bytes || a->bytes != c->bytes) { return fail(ctx, NB200_ERR_ARG, "fmadd: size does not match"); }
+	if(!same_shape(a, b) || !same_shape(a, c)) { return fail(ctx, NB200_ERR_ARG, "fmadd: size does not match"); }
 	if(a->lane_elems == 0) { return NB200_OK; }
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
@@ -1008,7 +1031,7 @@ int fused_terms(nb200_ctx* ctx, const char* who, nb200_buf* a, const nb200_buf* 
 		{
 			return fail(ctx, NB200_ERR_ARG, "%s: term %zu is not a buffer of this context", who, k);
 		}
-		if(terms[k]->bytes != a->bytes) { return fail(ctx, NB200_ERR_ARG, "%s: term %zu size does not match", who, k); }
+		if(!same_shape(terms[k], a)) { return fail(ctx, NB200_ERR_ARG, "%s: term %zu size does not match", who, k); }
 		used.push_back(k);
 	}
 	if(used.empty())
@@ -1064,7 +1087,7 @@ NB200_API int nb200_fmaddn(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, con
 	if(b != nullptr)
 	{
 		if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmaddn: b is not a buffer of this context"); }
-		if(a->bytes != b->bytes) { return fail(ctx, NB200_ERR_ARG, "fmaddn: size does not match"); }
+		if(!same_shape(a, b)) { return fail(ctx, NB200_ERR_ARG, "fmaddn: size does not match"); }
 	}
 	// Reference quirk kept: with b != NULL and no non-zero term, a is NOT assigned (nbody_engine.cpp:87-112).
 	return fused_terms(ctx, "fmaddn", a, b, nullptr, c, d, n, b != nullptr);
@@ -1076,7 +1099,7 @@ NB200_API int nb200_fmaddn_corr(nb200_ctx* ctx, nb200_buf* a, nb200_buf* corr, c
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: a is not a buffer of this context"); }
 	if(!valid(ctx, corr)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: corr is not a buffer of this context"); }
 	if(c == nullptr) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: c == NULL"); }
-	if(a->bytes != corr->bytes) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: size does not match"); }
+	if(!same_shape(a, corr)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: size does not match"); }
 	if(a == corr) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: a and corr must differ"); }
 	// The reference validates every b[k], zero coefficient or not (nbody_engine_cuda.cpp:431-439).
 	for(size_t k = 0; k < n; ++k)

@@ -99,8 +99,9 @@ struct nb200_ctx
 	long long	opt_timing = 1;
 	long long	opt_direct_sym = -1;	// -1 auto, 0 off, 1 force
 	long long	opt_sym_tile = 0;		// tile edge override (multiple of 256)
-	// bodies per lane (row x column): 0: 8 x 1, 1: 4 x 2, 2: 8 x 2, 3: 4 x 4; fastest measured: 4 x 2 (FP64), 8 x 2 (FP32)
-	long long	opt_sym_shape = sizeof(real) == 8 ? 1 : 2;
+	// bodies per lane (row x column): 0: 8 x 1, 1: 4 x 2, 2: 8 x 2, 3: 4 x 4; FP32 only: 4: 8 x 2 packed f32x2, 5: 4 x 2 packed.
+	// Fastest measured: 4 x 2 (FP64), 8 x 2 packed (FP32)
+	long long	opt_sym_shape = sizeof(real) == 8 ? 1 : 4;
 };
 
 struct nb200_buf

@@ -209,6 +209,156 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 	}
 }
 
+#if NB200_PRECISION == 1
+// ---- FP32 build: packed two-wide arithmetic (Blackwell fma.rn.f32x2 -> FFMA2 / FMUL2 / FADD2) -------------------------
+// The FP32 path is issue-bound, so the two column bodies a lane holds are kept as one packed f32x2 per component: one
+// instruction serves the pairs (row k, column 0) and (row k, column 1). 16 packed + 2 FMNMX + 2 MUFU.RSQ per two
+// unordered pairs (5 issue slots per interaction instead of 9). Row accumulators are packed partial sums (from column 0
+// and column 1), added when the row block is written.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi)
+{
+	f32x2 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c)
+{
+	f32x2 d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b)
+{
+	f32x2 d;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b)
+{
+	f32x2 d;
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ f32x2 f2_shfl(f32x2 v, int src_lane)
+{
+	return __shfl_sync(0xffffffffu, v, src_lane);
+}
+
+// Same tile algorithm as direct_sym_tiles<I, 2>, column pair packed.
+template<int I>
+__global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
+direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ tile_rc, float* __restrict__ p_row,
+					   float* __restrict__ p_col, int tile_edge)
+{
+	extern __shared__ float colacc[];	// [3][tile_edge]
+	const int	T = tile_edge;
+	const int	lane = threadIdx.x & 31;
+	const int	warp = threadIdx.x >> 5;
+	const int2	rc = tile_rc[blockIdx.x];
+	const bool	diagonal = rc.x == rc.y;
+	const body4* __restrict__ rows = src + static_cast<size_t>(rc.x) * T;
+	const body4* __restrict__ cols = src + static_cast<size_t>(rc.y) * T;
+	float*		out_row = p_row + static_cast<size_t>(blockIdx.x) * 3 * T;
+	float*		out_col = p_col + static_cast<size_t>(blockIdx.x) * 3 * T;
+	const int	n_ablk = T / (32 * I);
+	const int	n_bblk = T / 64;
+	const int	from = (lane + 31) & 31;
+
+	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	{
+		colacc[e] = 0;
+	}
+	__syncthreads();
+
+	for(int a0 = 0; a0 < n_ablk; a0 += NB200_SYM_WARPS)
+	{
+		const int	ablk = a0 + warp;
+		const bool	active = ablk < n_ablk;
+		f32x2 xa[I], ya[I], za[I], nma[I], ax[I], ay[I], az[I];
+#pragma unroll
+		for(int k = 0; k < I; ++k)
+		{
+			const body4 b = rows[(active ? ablk : 0) * 32 * I + k * 32 + lane];
+			xa[k] = f2_pack(b.x, b.x); ya[k] = f2_pack(b.y, b.y); za[k] = f2_pack(b.z, b.z);
+			nma[k] = f2_pack(-b.m, -b.m);
+			ax[k] = ay[k] = az[k] = f2_pack(0.f, 0.f);
+		}
+		int		bblk = (warp * (n_bblk / NB200_SYM_WARPS)) % n_bblk;
+		body4	nxt0 = cols[bblk * 64 + lane], nxt1 = cols[bblk * 64 + 32 + lane];
+		for(int p = 0; p < n_bblk; ++p)
+		{
+			if(active)
+			{
+			f32x2 xb = f2_pack(nxt0.x, nxt1.x), yb = f2_pack(nxt0.y, nxt1.y), zb = f2_pack(nxt0.z, nxt1.z);
+			f32x2 mb = f2_pack(nxt0.m, nxt1.m);
+			f32x2 bx = f2_pack(0.f, 0.f), by = bx, bz = bx;
+			const int	cur = bblk;
+			bblk = bblk + 1 == n_bblk ? 0 : bblk + 1;
+			if(p + 1 < n_bblk)
+			{
+				nxt0 = cols[bblk * 64 + lane];
+				nxt1 = cols[bblk * 64 + 32 + lane];
+			}
+#pragma unroll 1
+			for(int step = 0; step < 32; ++step)
+			{
+#pragma unroll
+				for(int k = 0; k < I; ++k)
+				{
+					f32x2	dx = f2_sub(xb, xa[k]), dy = f2_sub(yb, ya[k]), dz = f2_sub(zb, za[k]);
+					f32x2	r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+					float	r2l, r2h;
+					f2_unpack(r2, r2l, r2h);
+					f32x2	y = f2_pack(rsqrtf(fmaxf(r2l, NB200_MIN_DISTANCE)), rsqrtf(fmaxf(r2h, NB200_MIN_DISTANCE)));
+					f32x2	y3 = f2_mul(f2_mul(y, y), y);
+					f32x2	ca = f2_mul(mb, y3);
+					f32x2	ncb = f2_mul(nma[k], y3);
+					ax[k] = f2_fma(dx, ca, ax[k]);
+					ay[k] = f2_fma(dy, ca, ay[k]);
+					az[k] = f2_fma(dz, ca, az[k]);
+					bx = f2_fma(dx, ncb, bx);
+					by = f2_fma(dy, ncb, by);
+					bz = f2_fma(dz, ncb, bz);
+				}
+				xb = f2_shfl(xb, from); yb = f2_shfl(yb, from); zb = f2_shfl(zb, from); mb = f2_shfl(mb, from);
+				bx = f2_shfl(bx, from); by = f2_shfl(by, from); bz = f2_shfl(bz, from);
+			}
+			if(!diagonal)
+			{
+				float l0, l1;
+				const int c = cur * 64 + lane;
+				f2_unpack(bx, l0, l1); colacc[c] += l0; colacc[c + 32] += l1;
+				f2_unpack(by, l0, l1); colacc[T + c] += l0; colacc[T + c + 32] += l1;
+				f2_unpack(bz, l0, l1); colacc[2 * T + c] += l0; colacc[2 * T + c + 32] += l1;
+			}
+			}
+			__syncthreads();
+		}
+		if(active)
+		{
+#pragma unroll
+			for(int k = 0; k < I; ++k)
+			{
+				const int r = ablk * 32 * I + k * 32 + lane;
+				float l0, l1;
+				f2_unpack(ax[k], l0, l1); out_row[r] = l0 + l1;
+				f2_unpack(ay[k], l0, l1); out_row[T + r] = l0 + l1;
+				f2_unpack(az[k], l0, l1); out_row[2 * T + r] = l0 + l1;
+			}
+		}
+	}
+	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	{
+		out_col[e] = colacc[e];
+	}
+}
+#endif // NB200_PRECISION == 1
+
 // Index of tile (r, c), c >= r, in the row-major enumeration of the upper triangle of an S x S grid.
 __host__ __device__ __forceinline__ long long sym_tile_id(int r, int c, int S)
 {

@@ -205,12 +205,17 @@ def test_direct_symmetric_is_the_large_n_default(oracle64):
     assert np.all(np.abs(force) <= 1e-11 * scale)
 
 
-@pytest.mark.parametrize("n,tile", [(4096, 1024), (5000, 512)])
-def test_direct_symmetric_tiles_fp32(oracle32, oracle64, n, tile):
+@pytest.mark.parametrize("n,tile,shape", [(4096, 1024, 2), (5000, 512, 1), (4096, 1024, 4), (5000, 512, 5), (3000, 1024, 4)])
+def test_direct_symmetric_tiles_fp32(oracle32, oracle64, n, tile, shape):
+    """Shapes 4 and 5 are the packed fma.rn.f32x2 kernels (two column bodies per instruction)."""
     rng = np.random.RandomState(n)
     y = rng.uniform(-50, 50, 6 * n).astype(np.float32)
     m = rng.uniform(0.1, 2.0, n).astype(np.float32)
-    f = run_direct(y, m, precision="f32", options=(("direct_symmetric", 1), ("direct_sym_tile", tile)))
+    y[1] = y[0]
+    y[n + 1] = y[n]
+    y[2 * n + 1] = y[2 * n]            # bodies 0 and 1 coincide: clamped pair, exactly zero contribution
+    f = run_direct(y, m, precision="f32", options=(("direct_symmetric", 1), ("direct_sym_tile", tile), ("direct_sym_shape", shape)))
+    assert np.all(np.isfinite(f))
     ref32 = oracle32.fcompute_openmp(y, m)
     truth = oracle64.fcompute_openmp(y.astype(np.float64), m.astype(np.float64))
     assert np.array_equal(f[:3 * n], y[3 * n:])
