@@ -29,9 +29,10 @@
 //           (nbody_space_heap_stackless.cpp:3-28) -- results are bit-identical to the
 //           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape).
 //
-//   shards  with G shards (lanes or ranks) every shard builds the whole tree, walks the CONTIGUOUS leaves
-//           [g N/G, (g+1) N/G) -- a compact region, so warps stay coherent -- and writes leaf-ordered accelerations;
-//           one all-gather (3N reals) later each shard picks its own bodies through the inverse leaf map. The
+//   shards  with G shards (lanes or ranks) every shard builds the whole tree and walks chunks of 4096 CONSECUTIVE
+//           leaves dealt round-robin (a chunk is a compact region, so warps stay coherent; dealing evens out dense
+//           and sparse regions); one all-gather (3N reals) later each shard picks its own bodies through the
+//           inverse leaf map. The
 //           reference instead zero-fills f on every device and all-reduces all 6N values (synchronize_sum).
 //
 // The only library primitive is cub::DeviceRadixSort (3 presorts per rebuild); everything else is hand-written.
@@ -45,6 +46,7 @@
 
 #define NB200_BH_LOCAL 1024        // bodies per phase-B segment (one CTA)
 #define NB200_BH_PART_BLOCK 1024   // elements per partition block (256 threads x 4)
+#define NB200_BH_DEAL_CHUNK 4096   // consecutive leaves per chunk when the walk is dealt to several shards
 
 #if NB200_PRECISION == 2
 typedef double4 node4;	// 32 bytes
@@ -321,13 +323,23 @@ __global__ void __launch_bounds__(256) bh_leaf_positions(const int* __restrict__
 }
 
 // f = (v, a) for this shard's bodies from the gathered leaf-ordered accelerations
+// Leaf chunks of `chunk` consecutive leaves are dealt to the shards round-robin (dense and sparse regions of the tree
+// cost very different walk lengths; interleaving evens the shards out while a chunk is still a compact region):
+// leaf position p -> chunk c = p / chunk -> shard c % G, slot (c / G) * chunk + p % chunk of that shard's block.
+__device__ __forceinline__ size_t bh_leaf_slot(size_t p, size_t chunk, size_t nshards, size_t n_shard)
+{
+	const size_t c = p / chunk;
+	return (c % nshards) * 3 * n_shard + (c / nshards) * chunk + p % chunk;
+}
+
 __global__ void __launch_bounds__(256) bh_scatter_own(const real* __restrict__ acc_all, const int* __restrict__ leaf_pos,
-													   const real* __restrict__ y, real* __restrict__ f, size_t n_shard, size_t shard_first)
+													   const real* __restrict__ y, real* __restrict__ f, size_t n_shard, size_t shard_first,
+													   size_t chunk, size_t nshards)
 {
 	size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if(i >= n_shard) { return; }
 	const size_t p = static_cast<size_t>(leaf_pos[shard_first + i]);
-	const real*  a = acc_all + (p / n_shard) * 3 * n_shard + (p % n_shard);
+	const real*  a = acc_all + bh_leaf_slot(p, chunk, nshards, n_shard);
 	f[i] = y[3 * n_shard + i];
 	f[n_shard + i] = y[4 * n_shard + i];
 	f[2 * n_shard + i] = y[5 * n_shard + i];
@@ -402,13 +414,14 @@ __device__ __forceinline__ void node_force_from_test(real dx, real dy, real dz, 
 
 // one thread per target, independent stackless walks (the reference kernel's shape)
 __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
-													   const int* __restrict__ body_n, real* __restrict__ acc_leaf, int leaf_first,
+													   const int* __restrict__ body_n, real* __restrict__ acc_leaf, int3 deal,
 													   const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													   size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
 {
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if(t >= n_targets) { return; }
-	const int	leaf = n + leaf_first + t;
+	// deal = {chunk, shards, shard}: target t of this shard is leaf ((t / chunk) * shards + shard) * chunk + t % chunk
+	const int	leaf = n + ((t / deal.x) * deal.y + deal.z) * deal.x + t % deal.x;
 	const int	tree_size = 2 * n;
 	const node4	me = load_node(xyzr, leaf);
 	real		ax = 0, ay = 0, az = 0;
@@ -459,14 +472,15 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 #endif
 template<bool STATS>
 __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
-													 const int* __restrict__ body_n, real* __restrict__ acc_leaf, int leaf_first,
+													 const int* __restrict__ body_n, real* __restrict__ acc_leaf, int3 deal,
 													 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 													 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
 {
 	const int	t = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool	live = t < n_targets;
 	const int	tc = live ? t : n_targets - 1;	// idle lanes shadow the last target and never store
-	const int	leaf = n + leaf_first + tc;
+	// deal = {chunk, shards, shard}: target t of this shard is leaf ((t / chunk) * shards + shard) * chunk + t % chunk
+	const int	leaf = n + ((tc / deal.x) * deal.y + deal.z) * deal.x + tc % deal.x;
 	const int	tree_size = 2 * n;
 	const node4	me = load_node(xyzr, leaf);
 	real		ax = 0, ay = 0, az = 0;
@@ -688,22 +702,24 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	}
 	const int	n_targets = static_cast<int>(ctx->n_shard);
 	const int	shard_first = static_cast<int>(static_cast<size_t>(l.shard) * ctx->n_shard);
-	// one shard: results go straight to f by body index; several: contiguous leaves -> leaf-ordered block of acc_all
+	// one shard: results go straight to f by body index; several: chunks of consecutive leaves dealt round-robin,
+	// results into this shard's block of acc_all in the order walked
 	real*		acc_leaf = ctx->nshards > 1 ? s->acc_all + static_cast<size_t>(l.shard) * 3 * ctx->n_shard : nullptr;
-	const int	leaf_first = ctx->nshards > 1 ? shard_first : 0;
+	const int	chunk = static_cast<int>(std::min<size_t>(NB200_BH_DEAL_CHUNK, ctx->n_shard));
+	const int3	deal = make_int3(ctx->nshards > 1 ? chunk : n_targets, ctx->nshards, ctx->nshards > 1 ? l.shard : 0);
 	const int	block = (ctx->opt_walk_threads == 64 || ctx->opt_walk_threads == 256) ? static_cast<int>(ctx->opt_walk_threads) : 128;
 	const unsigned grid = static_cast<unsigned>((n_targets + block - 1) / block);
 	if(ctx->opt_walk_block == 1)
 	{
-		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, leaf_first, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}
 	else if(stats != nullptr)
 	{
-		bh_walk_warp<true><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, leaf_first, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		bh_walk_warp<true><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}
 	else
 	{
-		bh_walk_warp<false><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, leaf_first, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+		bh_walk_warp<false><<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}
 	++launches;
 	BH_CU(cudaGetLastError());
@@ -720,7 +736,8 @@ static int bh_scatter(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, int
 {
 	bh_state* s = l.bh;
 	bh_scatter_own<<<static_cast<unsigned>((ctx->n_shard + 255) / 256), 256, 0, l.stream>>>(
-		s->acc_all, s->leaf_pos, y, f, ctx->n_shard, static_cast<size_t>(l.shard) * ctx->n_shard);
+		s->acc_all, s->leaf_pos, y, f, ctx->n_shard, static_cast<size_t>(l.shard) * ctx->n_shard,
+		std::min<size_t>(NB200_BH_DEAL_CHUNK, ctx->n_shard), static_cast<size_t>(ctx->nshards));
 	++launches;
 	BH_CU(cudaGetLastError());
 	if(ctx->opt_timing) { BH_CU(cudaEventRecord(l.ev_t[4], l.stream)); }
