@@ -1333,7 +1333,7 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	if(ctx == nullptr || name == nullptr) { return NB200_ERR_ARG; }
 	if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
-	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_block = value; }	// 0 = warp-coherent, 1 = one thread per target
+	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = warp-coherent, 1 = one thread per target
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
 	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; }	// -1 auto, 0 off, 1 on
 	else if(strcmp(name, "direct_sym_tile") == 0) { ctx->opt_sym_tile = value; }

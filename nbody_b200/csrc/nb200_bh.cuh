@@ -57,7 +57,6 @@ typedef float4 node4;	// 16 bytes
 struct bh_state
 {
 	size_t	n = 0;
-	int		log2n = 0;
 	node4*	xyzr = nullptr;		// [2n]
 	real*	nmass = nullptr;	// [2n]
 	real*	bmin = nullptr;		// [2n][3]
@@ -78,7 +77,6 @@ struct bh_state
 	int*	leaf_pos = nullptr;	// [n] leaf position of every body (inverse of body_n[n..2n))
 	real*	acc_all = nullptr;	// [shards][3][n_shard] accelerations in leaf order
 	bool	have_tree = false;
-	real	built_ratio = 0;
 };
 
 static void bh_free(bh_state* s)
@@ -361,15 +359,6 @@ __device__ __forceinline__ node4 load_node(const node4* __restrict__ xyzr, int i
 #endif
 }
 
-// accepted node -> same force form as the direct kernel (clamp applied after the acceptance test, as in
-// kfcompute_heap_bh_stackless, nbody_engine_cuda_impl.cu:399-413)
-__device__ __forceinline__ void node_force(real px, real py, real pz, const node4& nd, real m, real& ax, real& ay, real& az)
-{
-	body4 s;
-	s.x = nd.x; s.y = nd.y; s.z = nd.z; s.m = m;
-	pair_interaction(px, py, pz, s, ax, ay, az);
-}
-
 __device__ __forceinline__ void store_f(const real* __restrict__ y, real* __restrict__ f, size_t n_shard, size_t li,
 										real ax, real ay, real az)
 {
@@ -459,11 +448,6 @@ __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ 
 		atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
 		atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
 	}
-}
-
-__device__ __forceinline__ void prefetch_l1(const void* p)
-{
-	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 // one warp per 32 consecutive targets, warp-uniform walk over the union of the lanes' traversals
@@ -556,7 +540,6 @@ static int bh_alloc(nb200_ctx* ctx, nb200_lane& l, std::string& err)
 	l.bh = nullptr;
 	bh_state* s = new bh_state();
 	s->n = n;
-	while((static_cast<size_t>(1) << s->log2n) < n) { ++s->log2n; }
 	const size_t nblk = n / NB200_BH_PART_BLOCK + 1;
 	bool ok = cudaMalloc(&s->xyzr, 2 * n * sizeof(node4)) == cudaSuccess &&
 			  cudaMalloc(&s->nmass, 2 * n * sizeof(real)) == cudaSuccess &&
@@ -667,7 +650,6 @@ static int bh_update_geometry(nb200_ctx* ctx, nb200_lane& l, int& launches, std:
 		++launches;
 	}
 	BH_CU(cudaGetLastError());
-	s->built_ratio = ctx->bh_ratio;
 	return NB200_OK;
 }
 
@@ -709,7 +691,7 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	const int3	deal = make_int3(ctx->nshards > 1 ? chunk : n_targets, ctx->nshards, ctx->nshards > 1 ? l.shard : 0);
 	const int	block = (ctx->opt_walk_threads == 64 || ctx->opt_walk_threads == 256) ? static_cast<int>(ctx->opt_walk_threads) : 128;
 	const unsigned grid = static_cast<unsigned>((n_targets + block - 1) / block);
-	if(ctx->opt_walk_block == 1)
+	if(ctx->opt_walk_mode == 1)
 	{
 		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}

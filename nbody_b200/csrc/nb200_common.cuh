@@ -94,7 +94,7 @@ struct nb200_ctx
 	// tunables (0 = automatic)
 	long long	opt_direct_ipt = 0;
 	long long	opt_direct_segments = 0;
-	long long	opt_walk_block = 0;	// walk_mode
+	long long	opt_walk_mode = 0;	// walk_mode
 	long long	opt_walk_threads = 0;
 	long long	opt_timing = 1;
 	long long	opt_direct_sym = -1;	// -1 auto, 0 off, 1 force
