@@ -157,3 +157,67 @@ def test_c1_rk4_drift_matches_openmp_engine(ref64, adapter):
         assert b[1][key] == pytest.approx(a[1][key], rel=1e-11)
     for key in ("dP", "dL", "dE"):
         assert abs(a[1][key] - b[1][key]) <= 1e-9            # per cent of the initial value
+
+
+def test_adaptive_rkdp_takes_the_same_decisions(ref64, adapter):
+    """Error-controlled rkdp (fmaxabs of the embedded error -> host branch -> step subdivision,
+    nbody_solver_rk_butcher.cpp:213-231) on b200 vs the reference's openmp engine: the same number of fcompute calls
+    (i.e. the same accept/subdivide decisions) and the same trajectory."""
+    from oracle import refharness as R
+    out = {}
+    for name, make in (("openmp", lambda: R.Engine(ref64, engine="openmp")),
+                       ("b200", lambda: b200_engine(ref64, adapter, engine="b200")),
+                       ("b200-2lanes", lambda: b200_engine(ref64, adapter, engine="b200", device="0,0"))):
+        d = R.Data(ref64).make_universe(512)                 # N = 1024
+        e = make()
+        assert e.init(d)
+        s = R.Solver(ref64, solver="rkdp", max_step=5e-2, min_step=1e-9, error_threshold=1e-6, max_recursion=6,
+                     substep_subdivisions=2, refine_steps_count=1)
+        s.set_engine(e)
+        assert s.run(d, 0.25) == 0
+        e.get_data(d)
+        y, _ = d.export()
+        out[name] = (e.compute_count(), y)
+        s.close()
+        e.close()
+        d.close()
+    assert out["openmp"][0] == out["b200"][0] == out["b200-2lanes"][0]
+    assert out["openmp"][0] > 7 * 5                          # subdivision really happened
+    assert np.abs(out["openmp"][1] - out["b200"][1]).max() <= 1e-9
+    assert np.array_equal(out["b200"][1], out["b200-2lanes"][1]) or np.abs(out["b200"][1] - out["b200-2lanes"][1]).max() <= 1e-12
+
+
+def test_fp32_adapter_euler_vs_reference_fp32(ref32):
+    """NB_COORD_PRECISION=1 twin: libnbody_engine_b200_f32 + libnb200_f32 driven by the FP32 build of the reference's
+    euler solver; trajectory vs the reference's own FP32 simple engine."""
+    from nbody_b200 import build
+    from oracle import refharness as R
+    path = build.adapter_path("f32")
+    if not os.path.exists(path):
+        pytest.skip("FP32 adapter not built")
+    ad = C.CDLL(path, mode=C.RTLD_LOCAL)
+    ad.nbody_engine_b200_create.restype = C.c_void_p
+    ad.nbody_engine_b200_create.argtypes = [C.c_char_p]
+    out = {}
+    for name in ("simple", "b200", "b200_bh"):
+        d = R.Data(ref32).make_universe(128)
+        if name == "simple":
+            e = R.Engine(ref32, engine="simple")
+        else:
+            kw = dict(engine=name) if name == "b200" else dict(engine=name, distance_to_node_radius_ratio=1e8)
+            h = ad.nbody_engine_b200_create(R.params(**kw))
+            assert h
+            e = R.Engine(ref32, handle=h)
+        assert e.init(d)
+        s = R.Solver(ref32, solver="euler", max_step=1e-2)
+        s.set_engine(e)
+        assert s.run(d, 0.05) == 0
+        e.get_data(d)
+        y, _ = d.export()
+        out[name] = y.astype(np.float64)
+        s.close()
+        e.close()
+        d.close()
+    scale = np.abs(out["simple"]).max()
+    assert np.abs(out["b200"] - out["simple"]).max() <= 2e-5 * scale
+    assert np.abs(out["b200_bh"] - out["simple"]).max() <= 2e-5 * scale
