@@ -337,6 +337,10 @@ NB200_API int nb200_create(nb200_ctx** out, const int* dev_ids, int nlanes, int 
 					if(r != cudaSuccess && r != cudaErrorPeerAccessAlreadyEnabled) { status = NB200_ERR_CUDA; }
 					cudaGetLastError();
 				}
+				else
+				{
+					ctx->peer_loads = false;	// gathers go through cudaMemcpyPeer staging; no symmetric-tile path
+				}
 			}
 		}
 	}
@@ -676,7 +680,8 @@ namespace {
 // Tile edge of the symmetric path for this problem, 0 = use the plain kernel.
 int sym_tile_edge(const nb200_ctx* ctx)
 {
-	if(ctx->lanes.size() != 1 || ctx->opt_direct_sym == 0) { return 0; }
+	if(ctx->opt_direct_sym == 0) { return 0; }
+	if(ctx->lanes.size() > 1 && (ctx->nranks > 1 || !ctx->peer_loads || ctx->lanes.size() > NB200_SYM_MAX_PEERS)) { return 0; }
 	if(ctx->opt_direct_sym < 0 && ctx->n < 32768) { return 0; }	// too few tiles to fill 148 SMs
 	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(3) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }	// partials > ~30 GB per rank
 	// automatic edge: ~N/128 (>= 8000 equal tiles), at most 8192 (192 KB of column sums; scratch 24 N^2 / T bytes)
@@ -692,12 +697,24 @@ int sym_tile_edge(const nb200_ctx* ctx)
 	return static_cast<int>(edge);
 }
 
-int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
+template<class Kernel>
+int sym_launch(nb200_ctx* ctx, nb200_lane& l, Kernel kernel, size_t tiles, size_t smem, int T)
 {
-	nb200_lane&		l = ctx->lanes[0];
+	CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+	kernel<<<static_cast<unsigned>(tiles), NB200_SYM_THREADS, smem, l.stream>>>(
+		l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+	LAUNCHED(ctx);
+	return NB200_OK;
+}
+
+// Tiles of shard `l.shard` (dealt round-robin over all shards) -> l.sym_acc = this shard's partial accelerations of
+// ALL bodies, laid out [shard][3][n_shard].
+int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
+{
 	const int		S = static_cast<int>((ctx->n + T - 1) / T);
 	const long long	total = static_cast<long long>(S) * (S + 1) / 2;
-	const size_t	mine = static_cast<size_t>((total - ctx->rank + ctx->nranks - 1) / ctx->nranks);
+	const int		G = ctx->nshards;
+	const size_t	mine = static_cast<size_t>((total - l.shard + G - 1) / G);
 	CU(ctx, cudaSetDevice(l.dev));
 	if(l.sym_edge != T || l.sym_ntiles != mine)
 	{
@@ -715,7 +732,7 @@ int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
 		{
 			for(int c = r; c < S; ++c, ++id)
 			{
-				if(id % ctx->nranks == ctx->rank) { rc.push_back(make_int2(r, c)); }
+				if(id % G == l.shard) { rc.push_back(make_int2(r, c)); }
 			}
 		}
 		const size_t tile_bytes = 3 * static_cast<size_t>(T) * sizeof(real);
@@ -736,64 +753,86 @@ int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
 	const size_t smem = 3 * static_cast<size_t>(T) * sizeof(real);
 	if(mine > 0)
 	{
+		int rc = NB200_OK;
+		switch(ctx->opt_sym_shape)
+		{
 #if NB200_PRECISION == 1
-		// FP32: packed f32x2 kernels for the two-column shapes (4: 8 x 2 packed, 5: 4 x 2 packed)
-		if(ctx->opt_sym_shape == 4)
-		{
-			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles_f32x2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			direct_sym_tiles_f32x2<8><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
-				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
-		}
-		else if(ctx->opt_sym_shape == 5)
-		{
-			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles_f32x2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			direct_sym_tiles_f32x2<4><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
-				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
-		}
-		else
+		case 4: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<8>, mine, smem, T); break;	// packed f32x2
+		case 5: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<4>, mine, smem, T); break;
 #endif
-		if(ctx->opt_sym_shape == 2)
-		{
-			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			direct_sym_tiles<8, 2><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
-				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
+		case 3: rc = sym_launch(ctx, l, direct_sym_tiles<4, 4>, mine, smem, T); break;
+		case 2: rc = sym_launch(ctx, l, direct_sym_tiles<8, 2>, mine, smem, T); break;
+		case 1: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2>, mine, smem, T); break;
+		default: rc = sym_launch(ctx, l, direct_sym_tiles<8, 1>, mine, smem, T); break;
 		}
-		else if(ctx->opt_sym_shape == 3)
-		{
-			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			direct_sym_tiles<4, 4><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
-				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
-		}
-		else if(ctx->opt_sym_shape == 1)
-		{
-			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			direct_sym_tiles<4, 2><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
-				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
-		}
-		else
-		{
-			CU(ctx, cudaFuncSetAttribute(direct_sym_tiles<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			direct_sym_tiles<8, 1><<<static_cast<unsigned>(mine), NB200_SYM_THREADS, smem, l.stream>>>(
-				l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
-		}
-		LAUNCHED(ctx);
+		if(rc != NB200_OK) { return rc; }
 	}
 	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[3], l.stream)); }
 	direct_sym_reduce<<<static_cast<unsigned>((ctx->n + 255) / 256), 256, 0, l.stream>>>(
-		l.sym_prow, l.sym_pcol, l.sym_acc, ctx->n, ctx->n_shard, T, S, ctx->rank, ctx->nranks);
+		l.sym_prow, l.sym_pcol, l.sym_acc, ctx->n, ctx->n_shard, T, S, l.shard, G);
 	LAUNCHED(ctx);
-	const real* acc = l.sym_acc;
-	if(ctx->nranks > 1)
+	return NB200_OK;
+}
+
+int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
+{
+	// phase 1: every lane turns its tiles into a partial acceleration vector over all bodies. A failed scratch
+	// allocation on a later lane only wastes the earlier lanes' launches: the caller reruns the step with the
+	// ordered-pair kernel, which overwrites f completely.
+	for(auto& l : ctx->lanes)
 	{
-		real* mine_acc = l.sym_acc + 3 * ctx->n;
-		NC(ctx, ctx->nccl->ReduceScatter(l.sym_acc, mine_acc, 3 * ctx->n_shard, NB200_NCCL_REAL, ncclSum,
-										 static_cast<ncclComm_t>(ctx->comm), l.stream));
-		acc = mine_acc;
+		int rc = sym_lane_partials(ctx, l, T);
+		if(rc != NB200_OK) { return rc; }
 	}
-	direct_sym_finish<<<static_cast<unsigned>((3 * ctx->n_shard + 255) / 256), 256, 0, l.stream>>>(
-		acc, lane_ptr(y, 0), lane_ptr(f, 0), ctx->n_shard);
-	LAUNCHED(ctx);
-	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }
+	const size_t	nl = ctx->lanes.size();
+	const unsigned	grid3 = static_cast<unsigned>((3 * ctx->n_shard + 255) / 256);
+	// phase 2: sum the partials of the own shard across shards
+	if(nl > 1)
+	{
+		sym_peers peers;
+		peers.count = static_cast<int>(nl);
+		for(size_t g = 0; g < nl; ++g) { peers.partial[g] = ctx->lanes[g].sym_acc; }
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			CU(ctx, cudaEventRecord(l.ev_packed, l.stream));	// "my partial vector is complete"
+		}
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			for(auto& p : ctx->lanes)
+			{
+				if(&p != &l) { CU(ctx, cudaStreamWaitEvent(l.stream, p.ev_packed, 0)); }
+			}
+			direct_sym_peer_sum<<<grid3, 256, 0, l.stream>>>(peers, l.sym_acc + 3 * ctx->n, ctx->n_shard, l.shard);
+			LAUNCHED(ctx);
+			CU(ctx, cudaEventRecord(l.ev_gathered, l.stream));	// "I no longer read the peers' partials"
+		}
+		for(auto& l : ctx->lanes)
+		{
+			CU(ctx, cudaSetDevice(l.dev));
+			for(auto& p : ctx->lanes)
+			{
+				if(&p != &l) { CU(ctx, cudaStreamWaitEvent(l.stream, p.ev_gathered, 0)); }
+			}
+		}
+	}
+	else if(ctx->nranks > 1)
+	{
+		nb200_lane& l = ctx->lanes[0];
+		NC(ctx, ctx->nccl->ReduceScatter(l.sym_acc, l.sym_acc + 3 * ctx->n, 3 * ctx->n_shard, NB200_NCCL_REAL, ncclSum,
+										 static_cast<ncclComm_t>(ctx->comm), l.stream));
+	}
+	// phase 3: f = (v, a)
+	for(size_t li = 0; li < nl; ++li)
+	{
+		nb200_lane& l = ctx->lanes[li];
+		CU(ctx, cudaSetDevice(l.dev));
+		const real* acc = ctx->nshards > 1 ? l.sym_acc + 3 * ctx->n : l.sym_acc;
+		direct_sym_finish<<<grid3, 256, 0, l.stream>>>(acc, lane_ptr(y, li), lane_ptr(f, li), ctx->n_shard);
+		LAUNCHED(ctx);
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }
+	}
 	return NB200_OK;
 }
 }  // namespace

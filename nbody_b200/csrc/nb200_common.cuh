@@ -85,6 +85,7 @@ struct nb200_ctx
 	std::unordered_set<const nb200_buf*>	live;
 	unsigned long long	launches = 0;
 	int			last_direct_path = 0;
+	bool		peer_loads = true;	// every lane can load from every other lane's memory (same device or peer access enabled)
 	std::string	err;
 	// Barnes-Hut configuration
 	real		bh_ratio = 10;

@@ -408,6 +408,30 @@ __global__ void __launch_bounds__(256) direct_sym_reduce(const real* __restrict_
 	o[2 * n_shard] = acc[2];
 }
 
+// Lanes of one process (NVLink peers or the same device): shard `shard` sums its block of every lane's partial vector
+// straight out of the peers' memory (plain loads on peer-mapped pointers), lanes in ascending order -> fixed order.
+#define NB200_SYM_MAX_PEERS 16
+struct sym_peers
+{
+	const real*	partial[NB200_SYM_MAX_PEERS];	// each [shards][3][n_shard]
+	int			count;
+};
+__global__ void __launch_bounds__(256) direct_sym_peer_sum(const sym_peers peers, real* __restrict__ mine, size_t n_shard, int shard)
+{
+	const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(e >= 3 * n_shard)
+	{
+		return;
+	}
+	const size_t off = static_cast<size_t>(shard) * 3 * n_shard + e;
+	real acc = 0;
+	for(int g = 0; g < peers.count; ++g)
+	{
+		acc += peers.partial[g][off];
+	}
+	mine[e] = acc;
+}
+
 // f = (v, a) for the local shard from an acceleration block laid out [3][n_shard]
 __global__ void __launch_bounds__(256) direct_sym_finish(const real* __restrict__ acc, const real* __restrict__ y,
 														 real* __restrict__ f, size_t n_shard)

@@ -17,6 +17,12 @@ for opts in ((), (("direct_symmetric",1),("direct_sym_tile",512)), (("direct_sym
         e.fmaddn(f, e.get_y(), ks, np.array([0.1, 0.0, 0.3]))
         e.fmaddn_corr(f, ks[0], ks[1:], np.array([0.5, 0.25]))
         print(opts, e.fmaxabs(f))
+with Engine(devices="0,0") as e:       # symmetric tiles across lanes: peer-sum kernel
+    e.set_option("direct_symmetric", 1); e.set_option("direct_sym_tile", 512)
+    assert e.init(y, m)
+    f = e.create_buffer(e.get_y().size()); g = e.create_buffer(e.get_y().size())
+    e.fcompute(0, e.get_y(), f); e.fcompute(0, f, g); e.fcompute(0, e.get_y(), g)
+    print("sym lanes", e.last_direct_path(), e.fmaxabs(g))
 with Engine(kind="bh", devices="0,0") as e:
     assert e.init(y, m)
     f = e.create_buffer(e.get_y().size())

@@ -179,6 +179,33 @@ def test_direct_symmetric_tiles_vs_oracle(oracle64, n, tile, shape):
     assert np.array_equal(f, again)                     # fixed summation order: bit-reproducible
 
 
+@pytest.mark.parametrize("devices,n,tile", [("0,0", 4096, 1024), ("0,0,0", 6144, 512), ("0,0,0,0", 8192, 1024)])
+def test_direct_symmetric_tiles_across_lanes(oracle64, devices, n, tile):
+    """Lanes of one process deal the tiles round-robin; each lane sums its body block of every lane's partial vector
+    straight from the peers' memory, lanes in ascending order. Two fcomputes back to back exercise the
+    'peers finished reading my partials' events."""
+    rng = np.random.RandomState(n)
+    y = rng.uniform(-50, 50, 6 * n)
+    m = rng.uniform(0.1, 2.0, n)
+    opts = (("direct_symmetric", 1), ("direct_sym_tile", tile))
+    from nbody_b200 import Engine
+    with Engine(devices=devices) as e:
+        for k, v in opts:
+            e.set_option(k, v)
+        assert e.init(y, m)
+        f1 = e.create_buffer(e.get_y().size())
+        f2 = e.create_buffer(e.get_y().size())
+        e.fcompute(0.0, e.get_y(), f1)
+        e.fcompute(0.0, f1, f2)            # different input, same scratch, no host sync in between
+        e.fcompute(0.0, e.get_y(), f2)
+        assert e.last_direct_path() == tile
+        a, b = e.read_buffer(f1), e.read_buffer(f2)
+    assert np.array_equal(a, b)
+    ref = oracle64.fcompute_openmp(y, m)
+    assert rel_err_per_body(a, ref, n) <= TOL64
+    assert rel_err_per_body(a, run_direct(y, m, options=opts), n) <= 1e-13
+
+
 def test_direct_symmetric_golden_universe():
     g = load_golden_npz("g1_n2048")
     f = run_direct(g["y"], g["mass"], options=(("direct_symmetric", 1), ("direct_sym_tile", 512)))
