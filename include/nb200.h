@@ -174,6 +174,28 @@ int nb200_clamp(nb200_ctx* ctx, nb200_buf* y, nb200_real b);
  * Always double, host-visible on return. With nranks > 1 every rank receives the global sums. */
 int nb200_statistics(nb200_ctx* ctx, const nb200_buf* y, int with_energy, double out[11]);
 
+/* ---- body arrays <-> state vector ------------------------------------------------------------
+ * The AoS <-> [rx|ry|rz|vx|vy|vz] transposes of nbody_engine_cuda::init / get_data (nbody_engine_cuda.cpp:113-139,
+ * 141-175: host loops over a full-buffer copy) done on the device: pos_xyz / vel_xyz are the N x 3 arrays behind
+ * nbody_data::get_vertites() / get_velosites(); each shard moves its contiguous body range with two DMA copies.
+ * nb200_host_register pins such an array once (cudaHostRegister), so the copies go at PCIe speed without staging. */
+int nb200_write_bodies(nb200_ctx* ctx, nb200_buf* y, const nb200_real* pos_xyz, const nb200_real* vel_xyz);
+int nb200_read_bodies(nb200_ctx* ctx, const nb200_buf* y, nb200_real* pos_xyz, nb200_real* vel_xyz);
+int nb200_host_register(nb200_ctx* ctx, void* host, size_t bytes);
+int nb200_host_unregister(nb200_ctx* ctx, void* host);
+
+/* ---- solver steps as CUDA graphs ---------------------------------------------------------------
+ * With nb200_set_option(ctx, "step_graph", 1) the library watches the calls between two step boundaries. A step
+ * that repeats the previous one call for call (same operations, buffers and scalars, nothing host-visible inside:
+ * every fixed-step solver of the reference, e.g. nbody_solver_rk4.cpp:30-62) is captured once into a CUDA graph and
+ * from then on launched as ONE graph per step; any deviation falls back to issuing the calls one by one, so results
+ * never differ from the eager engine. The adapter calls nb200_step_boundary from advise_time(), which every solver
+ * calls exactly once at the end of a step. Single-shard contexts only (ignored with lanes or ranks). */
+int nb200_step_boundary(nb200_ctx* ctx);
+/* out[0] = graphs launched, out[1] = replays abandoned, out[2] = state (0 off, 1 record, 2 capture, 3 replay),
+ * out[3] = kernel launches inside one replayed step. */
+int nb200_step_graph_stats(const nb200_ctx* ctx, unsigned long long out[4]);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of nb200 kernels launched since creation (all lanes). */
 unsigned long long nb200_launch_count(const nb200_ctx* ctx);
@@ -192,7 +214,7 @@ int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms);
  * ~`ms` milliseconds and returns achieved FMA instructions (per lane) per second. */
 int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s);
 /* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "walk_mode" (0 = warp-coherent walk,
- * 1 = one thread per target), "timing" (0/1: phase events). 0 = automatic where applicable. */
+ * 1 = one thread per target), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
 int nb200_set_option(nb200_ctx* ctx, const char* name, long long value);
 
 #ifdef __cplusplus

@@ -19,6 +19,7 @@
 #include "nb200_stateops.cuh"
 #include "nb200_bh.cuh"
 #include "nb200_stats.cuh"
+#include "nb200_stepgraph.cuh"
 
 #define NB200_API extern "C" __attribute__((visibility("default")))
 
@@ -219,6 +220,275 @@ void launch_pairs(nb200_ctx* ctx, nb200_lane& l, const real* y, real* out, dim3 
 		l.src, y, out, ctx->n_shard, static_cast<size_t>(l.shard) * ctx->n_shard, n_tiles, tiles_per_seg, write_f);
 }
 
+// ---- solver steps as CUDA graphs (nb200_stepgraph.cuh) -----------------------------------------------------------
+int step_issue(nb200_ctx* ctx, const step_op& op)
+{
+	nb200_buf* a = const_cast<nb200_buf*>(op.a);
+	switch(op.kind)
+	{
+	case SOP_FCOMPUTE_DIRECT: return nb200_fcompute_direct(ctx, op.a, const_cast<nb200_buf*>(op.b));
+	case SOP_FCOMPUTE_BH: return nb200_fcompute_bh(ctx, op.a, const_cast<nb200_buf*>(op.b), op.step);
+	case SOP_FMADD_INPLACE: return nb200_fmadd_inplace(ctx, a, op.b, op.coef[0]);
+	case SOP_FMADD: return nb200_fmadd(ctx, a, op.b, op.c, op.coef[0]);
+	case SOP_FMADDN_INPLACE: return nb200_fmaddn_inplace(ctx, a, op.list.data(), op.coef.data(), op.coef.size());
+	case SOP_FMADDN: return nb200_fmaddn(ctx, a, op.b, op.list.data(), op.coef.data(), op.coef.size());
+	case SOP_FMADDN_CORR: return nb200_fmaddn_corr(ctx, a, const_cast<nb200_buf*>(op.b), op.list.data(), op.coef.data(), op.coef.size());
+	case SOP_COPY: return nb200_copy(ctx, a, op.b);
+	case SOP_FILL: return nb200_fill(ctx, a, op.coef[0]);
+	case SOP_CLAMP: return nb200_clamp(ctx, a, op.coef[0]);
+	case SOP_FMAXABS: return NB200_OK;	// a segment border: ran when it was called
+	default: return fail(ctx, NB200_ERR_STATE, "step graph: unknown recorded call %d", op.kind);
+	}
+}
+
+void step_drop_graphs(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	bool synced = false;
+	for(cudaGraphExec_t e : sg.execs)
+	{
+		if(e == nullptr) { continue; }
+		if(!synced)
+		{
+			cudaSetDevice(ctx->lanes[0].dev);
+			cudaStreamSynchronize(ctx->lanes[0].stream);	// a launched graph may still be running
+			synced = true;
+		}
+		cudaGraphExecDestroy(e);
+	}
+	sg.execs.clear();
+	sg.seg_launches.clear();
+}
+
+void step_failure(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	if(++sg.failures > NB200_STEP_GRAPH_MAX_FAILURES)
+	{
+		step_drop_graphs(ctx);
+		sg.seq.clear();
+		sg.cur.clear();
+		sg.mode = SG_OFF;	// this caller's steps do not repeat: stay eager
+	}
+}
+
+// Issue ops[first, last) eagerly, in order (the library's own entry points, with deferral switched off meanwhile).
+int step_issue_range(nb200_ctx* ctx, const std::vector<step_op>& ops, size_t first, size_t last)
+{
+	step_graph& sg = *ctx->sg;
+	sg.busy = true;
+	int rc = NB200_OK;
+	for(size_t k = first; k < last && rc == NB200_OK; ++k) { rc = step_issue(ctx, ops[k]); }
+	sg.busy = false;
+	return rc;
+}
+
+// Replay ends early: the calls accepted since the last segment border have not run yet. Run them, then carry on as a
+// recording (earlier segments of this step already ran as graphs).
+int step_bail(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	const size_t first = sg.seg_start, upto = sg.pos;
+	++sg.bailouts;
+	sg.mode = SG_RECORD;
+	step_drop_graphs(ctx);
+	int rc = step_issue_range(ctx, sg.seq, first, upto);
+	sg.cur.assign(sg.seq.begin(), sg.seq.begin() + static_cast<std::ptrdiff_t>(upto));
+	sg.seq.clear();
+	sg.pos = sg.seg = sg.seg_start = 0;
+	step_failure(ctx);
+	return rc;
+}
+
+int step_begin_segment(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	nb200_lane& l = ctx->lanes[0];
+	CU(ctx, cudaSetDevice(l.dev));
+	CU(ctx, cudaStreamBeginCapture(l.stream, cudaStreamCaptureModeRelaxed));
+	sg.capturing = true;
+	sg.saved_timing = ctx->opt_timing;
+	ctx->opt_timing = 0;	// phase events cannot be read back from inside a graph
+	sg.launches_at_begin = ctx->launches;
+	sg.cur_seg_start = sg.cur.size();
+	return NB200_OK;
+}
+
+// Close the segment being captured (if any), run it, and keep its graph as segment number execs.size().
+int step_close_segment(nb200_ctx* ctx)
+{
+	step_graph&	sg = *ctx->sg;
+	if(!sg.capturing)
+	{
+		sg.execs.push_back(nullptr);	// an empty segment (two borders in a row, or a border first)
+		sg.seg_launches.push_back(0);
+		return NB200_OK;
+	}
+	nb200_lane&	l = ctx->lanes[0];
+	cudaGraph_t	graph = nullptr;
+	sg.capturing = false;
+	ctx->opt_timing = sg.saved_timing;
+	cudaSetDevice(l.dev);
+	cudaError_t		res = cudaStreamEndCapture(l.stream, &graph);
+	cudaGraphExec_t	exec = nullptr;
+	if(res == cudaSuccess) { res = cudaGraphInstantiate(&exec, graph, 0); }
+	if(res == cudaSuccess) { res = cudaGraphLaunch(exec, l.stream); }
+	if(graph != nullptr) { cudaGraphDestroy(graph); }
+	if(res != cudaSuccess)
+	{
+		// nothing of this segment has run: run it eagerly and stop deferring for good
+		cudaGetLastError();
+		if(exec != nullptr) { cudaGraphExecDestroy(exec); }
+		sg.mode = SG_OFF;
+		step_drop_graphs(ctx);
+		std::vector<step_op> lost;
+		lost.swap(sg.cur);
+		sg.seq.clear();
+		ctx->launches = sg.launches_at_begin;
+		int rc = step_issue_range(ctx, lost, sg.cur_seg_start, lost.size());
+		if(rc != NB200_OK) { return rc; }
+		ctx->err = std::string("step graph: capture failed (") + cudaGetErrorString(res) + "), continuing eagerly";
+		return NB200_OK;
+	}
+	sg.execs.push_back(exec);
+	sg.seg_launches.push_back(ctx->launches - sg.launches_at_begin);
+	++sg.graph_launches;
+	return NB200_OK;
+}
+
+// A host-visible or state-changing call: everything deferred so far must have been issued before it.
+int step_break(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
+	int rc = NB200_OK;
+	if(sg.mode == SG_REPLAY)
+	{
+		if(sg.pos == 0) { return NB200_OK; }	// between steps: nothing is deferred
+		rc = step_bail(ctx);
+	}
+	else if(sg.mode == SG_CAPTURE && !sg.cur.empty())
+	{
+		rc = step_close_segment(ctx);
+		if(sg.mode != SG_OFF)
+		{
+			step_drop_graphs(ctx);
+			sg.mode = SG_RECORD;
+			step_failure(ctx);
+		}
+	}
+	if(!sg.cur.empty()) { sg.clean = false; }
+	return rc;
+}
+
+// Buffers or configuration changed: a recorded step no longer describes what the caller will do.
+int step_invalidate(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
+	int rc = step_break(ctx);
+	if(sg.mode == SG_OFF) { return rc; }
+	step_drop_graphs(ctx);
+	sg.seq.clear();
+	sg.pos = sg.seg = sg.seg_start = 0;
+	sg.mode = SG_RECORD;
+	return rc;
+}
+
+int step_overflow(nb200_ctx* ctx)
+{
+	// nobody marks step boundaries: stop watching
+	step_graph& sg = *ctx->sg;
+	int rc = sg.capturing ? step_close_segment(ctx) : NB200_OK;
+	step_drop_graphs(ctx);
+	sg.cur.clear();
+	sg.seq.clear();
+	sg.mode = SG_OFF;
+	return rc;
+}
+
+// Every deferrable call reports itself here after validating its arguments. *skip: the call is part of the replayed
+// step and must not be issued now.
+int step_note(nb200_ctx* ctx, const step_op& op, bool* skip)
+{
+	step_graph& sg = *ctx->sg;
+	*skip = false;
+	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
+	if(sg.mode == SG_REPLAY)
+	{
+		if(sg.pos < sg.seq.size() && sg.seq[sg.pos].same(op))
+		{
+			++sg.pos;
+			*skip = true;
+			return NB200_OK;
+		}
+		int rc = step_bail(ctx);
+		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+	}
+	if(sg.mode == SG_CAPTURE && !sg.capturing)
+	{
+		int rc = step_begin_segment(ctx);
+		if(rc != NB200_OK) { return rc; }
+	}
+	sg.cur.push_back(op);
+	return sg.cur.size() > 65536 ? step_overflow(ctx) : NB200_OK;
+}
+
+// fmaxabs: host-visible, but part of every step of the error-controlled solvers (nbody_solver_rk_butcher.cpp:207-215).
+// It is a segment BORDER: what was deferred before it runs as one graph, the reduction itself runs right away, and
+// the calls after it form the next segment -- provided the solver then takes the same branch as in the recorded step.
+int step_border(nb200_ctx* ctx, const step_op& op)
+{
+	step_graph& sg = *ctx->sg;
+	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
+	if(sg.mode == SG_REPLAY)
+	{
+		if(sg.pos < sg.seq.size() && sg.seq[sg.pos].same(op))
+		{
+			nb200_lane& l = ctx->lanes[0];
+			if(sg.execs[sg.seg] != nullptr)
+			{
+				CU(ctx, cudaSetDevice(l.dev));
+				CU(ctx, cudaGraphLaunch(sg.execs[sg.seg], l.stream));
+				ctx->launches += sg.seg_launches[sg.seg];
+				++sg.graph_launches;
+			}
+			++sg.seg;
+			++sg.pos;
+			sg.seg_start = sg.pos;
+			return NB200_OK;
+		}
+		if(sg.pos == 0) { return NB200_OK; }	// a stray reduction between steps
+		int rc = step_bail(ctx);
+		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+	}
+	if(sg.mode == SG_CAPTURE)
+	{
+		int rc = step_close_segment(ctx);
+		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+	}
+	sg.cur.push_back(op);
+	return sg.cur.size() > 65536 ? step_overflow(ctx) : NB200_OK;
+}
+
+#define STEP_NOTE(ctx, op)                                                                             \
+	do                                                                                                 \
+	{                                                                                                  \
+		bool step_skip_ = false;                                                                       \
+		int step_rc_ = step_note(ctx, op, &step_skip_);                                                \
+		if(step_rc_ != NB200_OK || step_skip_) { return step_rc_; }                                    \
+	} while(0)
+
+step_op make_op(int kind, const nb200_buf* a, const nb200_buf* b = nullptr, const nb200_buf* c = nullptr)
+{
+	step_op op;
+	op.kind = kind;
+	op.a = a;
+	op.b = b;
+	op.c = c;
+	return op;
+}
+
 }  // namespace
 
 // ---- library / device queries ------------------------------------------------
@@ -286,6 +556,7 @@ NB200_API int nb200_create(nb200_ctx** out, const int* dev_ids, int nlanes, int 
 		}
 	}
 	nb200_ctx* ctx = new nb200_ctx();
+	ctx->sg = new step_graph();
 	ctx->rank = rank;
 	ctx->nranks = nranks;
 	ctx->nshards = nlanes * nranks;
@@ -379,6 +650,12 @@ NB200_API int nb200_create(nb200_ctx** out, const int* dev_ids, int nlanes, int 
 NB200_API int nb200_destroy(nb200_ctx* ctx)
 {
 	if(ctx == nullptr) { return NB200_OK; }
+	if(ctx->sg != nullptr && !ctx->lanes.empty() && ctx->lanes[0].stream != nullptr)
+	{
+		step_invalidate(ctx);	// issues whatever a replayed step still holds back
+		step_drop_graphs(ctx);
+		ctx->sg->mode = SG_OFF;
+	}
 	for(auto& l : ctx->lanes)
 	{
 		cudaSetDevice(l.dev);
@@ -402,6 +679,7 @@ NB200_API int nb200_destroy(nb200_ctx* ctx)
 		if(l.stream) { cudaStreamDestroy(l.stream); }
 	}
 	cudaGetLastError();
+	delete ctx->sg;
 	delete ctx;
 	return NB200_OK;
 }
@@ -414,6 +692,7 @@ NB200_API const char* nb200_last_error(const nb200_ctx* ctx)
 NB200_API int nb200_sync(nb200_ctx* ctx)
 {
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	step_break(ctx);
 	for(auto& l : ctx->lanes)
 	{
 		CU(ctx, cudaSetDevice(l.dev));
@@ -455,6 +734,7 @@ NB200_API int nb200_set_bodies(nb200_ctx* ctx, size_t n, const nb200_real* mass)
 {
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(n == 0 || mass == nullptr) { return fail(ctx, NB200_ERR_ARG, "set_bodies: empty body set"); }
+	step_invalidate(ctx);
 	if(n % static_cast<size_t>(ctx->nshards) != 0)
 	{
 		return fail(ctx, NB200_ERR_ARG, "set_bodies: N = %zu is not a multiple of the shard count %d", n, ctx->nshards);
@@ -497,6 +777,7 @@ NB200_API int nb200_get_mass(nb200_ctx* ctx, nb200_real* mass)
 {
 	if(ctx == nullptr || mass == nullptr) { return NB200_ERR_ARG; }
 	if(ctx->n == 0) { return fail(ctx, NB200_ERR_STATE, "get_mass: no bodies"); }
+	step_break(ctx);
 	nb200_lane& l = ctx->lanes[0];
 	CU(ctx, cudaSetDevice(l.dev));
 	CU(ctx, cudaMemcpyAsync(mass, l.mass, ctx->n * sizeof(real), cudaMemcpyDeviceToHost, l.stream));
@@ -509,6 +790,7 @@ NB200_API int nb200_alloc(nb200_ctx* ctx, size_t bytes, nb200_buf** out)
 {
 	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
 	*out = nullptr;
+	step_invalidate(ctx);	// a new handle may reuse the address of one a recorded step refers to
 	nb200_buf* b = new nb200_buf();
 	b->owner = ctx;
 	b->bytes = bytes;
@@ -540,6 +822,7 @@ NB200_API int nb200_free(nb200_ctx* ctx, nb200_buf* b)
 {
 	if(b == nullptr) { return NB200_OK; }
 	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "free: not a buffer of this context"); }
+	step_invalidate(ctx);
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		cudaSetDevice(ctx->lanes[i].dev);
@@ -571,6 +854,7 @@ NB200_API int nb200_write(nb200_ctx* ctx, nb200_buf* dst, const void* host)
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, dst)) { return fail(ctx, NB200_ERR_ARG, "write: dst is not a buffer of this context"); }
 	if(host == nullptr) { return fail(ctx, NB200_ERR_ARG, "write: NULL source"); }
+	step_break(ctx);
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];
@@ -595,6 +879,7 @@ NB200_API int nb200_read(nb200_ctx* ctx, void* host, const nb200_buf* src)
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, src)) { return fail(ctx, NB200_ERR_ARG, "read: src is not a buffer of this context"); }
 	if(host == nullptr) { return fail(ctx, NB200_ERR_ARG, "read: NULL destination"); }
+	step_break(ctx);
 	if(!src->sharded)
 	{
 		nb200_lane& l = ctx->lanes[0];
@@ -644,6 +929,107 @@ NB200_API int nb200_read(nb200_ctx* ctx, void* host, const nb200_buf* src)
 	return nb200_sync(ctx);
 }
 
+namespace {
+int ensure_read_scratch(nb200_ctx* ctx, nb200_lane& l, size_t bytes)
+{
+	if(l.read_scratch_bytes >= bytes) { return NB200_OK; }
+	if(l.read_scratch) { cudaFree(l.read_scratch); l.read_scratch = nullptr; l.read_scratch_bytes = 0; }
+	if(cudaMalloc(&l.read_scratch, bytes) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return fail(ctx, NB200_ERR_ALLOC, "staging allocation of %zu bytes failed", bytes);
+	}
+	l.read_scratch_bytes = bytes;
+	return NB200_OK;
+}
+}  // namespace
+
+// ---- body arrays <-> state vector (the get_data / init side of the engine) --------------------------
+NB200_API int nb200_host_register(nb200_ctx* ctx, void* host, size_t bytes)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(host == nullptr || bytes == 0) { return fail(ctx, NB200_ERR_ARG, "host_register: empty range"); }
+	cudaError_t res = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
+	if(res != cudaSuccess && res != cudaErrorHostMemoryAlreadyRegistered)
+	{
+		cudaGetLastError();
+		return fail(ctx, NB200_ERR_CUDA, "host_register: %s", cudaGetErrorString(res));
+	}
+	cudaGetLastError();
+	return NB200_OK;
+}
+
+NB200_API int nb200_host_unregister(nb200_ctx* ctx, void* host)
+{
+	if(ctx == nullptr || host == nullptr) { return NB200_ERR_ARG; }
+	cudaHostUnregister(host);
+	cudaGetLastError();	// not registered: nothing to undo
+	return NB200_OK;
+}
+
+NB200_API int nb200_write_bodies(nb200_ctx* ctx, nb200_buf* y, const nb200_real* pos_xyz, const nb200_real* vel_xyz)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "write_bodies: y is not a buffer of this context"); }
+	if(ctx->n == 0 || !y->sharded) { return fail(ctx, NB200_ERR_ARG, "write_bodies: y must be a state vector of 6*N elements"); }
+	if(pos_xyz == nullptr || vel_xyz == nullptr) { return fail(ctx, NB200_ERR_ARG, "write_bodies: NULL source"); }
+	step_break(ctx);
+	const size_t	n3 = 3 * ctx->n_shard;
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		int rc = ensure_read_scratch(ctx, l, 2 * n3 * sizeof(real));
+		if(rc != NB200_OK) { return rc; }
+		const size_t first = static_cast<size_t>(l.shard) * n3;	// a shard is a contiguous range of bodies
+		CU(ctx, cudaMemcpyAsync(l.read_scratch, pos_xyz + first, n3 * sizeof(real), cudaMemcpyHostToDevice, l.stream));
+		CU(ctx, cudaMemcpyAsync(l.read_scratch + n3, vel_xyz + first, n3 * sizeof(real), cudaMemcpyHostToDevice, l.stream));
+		ew_bodies_to_state<<<static_cast<unsigned>((2 * n3 + NB200_EW_THREADS - 1) / NB200_EW_THREADS), NB200_EW_THREADS, 0, l.stream>>>(
+			l.read_scratch, lane_ptr(y, i), ctx->n_shard);
+		LAUNCHED(ctx);
+	}
+	return nb200_sync(ctx);	// host memory may be reused as soon as we return
+}
+
+NB200_API int nb200_read_bodies(nb200_ctx* ctx, const nb200_buf* y, nb200_real* pos_xyz, nb200_real* vel_xyz)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "read_bodies: y is not a buffer of this context"); }
+	if(ctx->n == 0 || !y->sharded) { return fail(ctx, NB200_ERR_ARG, "read_bodies: y must be a state vector of 6*N elements"); }
+	if(pos_xyz == nullptr || vel_xyz == nullptr) { return fail(ctx, NB200_ERR_ARG, "read_bodies: NULL destination"); }
+	step_break(ctx);
+	const size_t	n3 = 3 * ctx->n_shard;
+	const size_t	blocks = ctx->nranks > 1 ? static_cast<size_t>(ctx->nshards) + 1 : 1;	// own block + the gathered ones
+	for(size_t i = 0; i < ctx->lanes.size(); ++i)
+	{
+		nb200_lane& l = ctx->lanes[i];
+		CU(ctx, cudaSetDevice(l.dev));
+		int rc = ensure_read_scratch(ctx, l, blocks * 2 * n3 * sizeof(real));
+		if(rc != NB200_OK) { return rc; }
+		ew_state_to_bodies<<<static_cast<unsigned>((2 * n3 + NB200_EW_THREADS - 1) / NB200_EW_THREADS), NB200_EW_THREADS, 0, l.stream>>>(
+			lane_ptr(y, i), l.read_scratch, ctx->n_shard);
+		LAUNCHED(ctx);
+		if(ctx->nranks > 1)
+		{
+			real* all = l.read_scratch + 2 * n3;
+			NC(ctx, ctx->nccl->AllGather(l.read_scratch, all, 2 * n3, NB200_NCCL_REAL, static_cast<ncclComm_t>(ctx->comm), l.stream));
+			for(int g = 0; g < ctx->nshards; ++g)
+			{
+				const real* blk = all + static_cast<size_t>(g) * 2 * n3;
+				CU(ctx, cudaMemcpyAsync(pos_xyz + static_cast<size_t>(g) * n3, blk, n3 * sizeof(real), cudaMemcpyDeviceToHost, l.stream));
+				CU(ctx, cudaMemcpyAsync(vel_xyz + static_cast<size_t>(g) * n3, blk + n3, n3 * sizeof(real), cudaMemcpyDeviceToHost, l.stream));
+			}
+		}
+		else
+		{
+			const size_t first = static_cast<size_t>(l.shard) * n3;
+			CU(ctx, cudaMemcpyAsync(pos_xyz + first, l.read_scratch, n3 * sizeof(real), cudaMemcpyDeviceToHost, l.stream));
+			CU(ctx, cudaMemcpyAsync(vel_xyz + first, l.read_scratch + n3, n3 * sizeof(real), cudaMemcpyDeviceToHost, l.stream));
+		}
+	}
+	return nb200_sync(ctx);
+}
+
 NB200_API int nb200_copy(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b)
 {
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
@@ -651,6 +1037,7 @@ NB200_API int nb200_copy(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b)
 	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "copy: b is not a buffer of this context"); }
 	if(!same_shape(a, b)) { return fail(ctx, NB200_ERR_ARG, "copy: size does not match"); }
 	if(a == b || a->lane_bytes == 0) { return NB200_OK; }
+	STEP_NOTE(ctx, make_op(SOP_COPY, a, b));
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];
@@ -660,11 +1047,24 @@ NB200_API int nb200_copy(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b)
 	return NB200_OK;
 }
 
+namespace {
+int fill_lanes(nb200_ctx* ctx, nb200_buf* a, real value);
+}
+
 NB200_API int nb200_fill(nb200_ctx* ctx, nb200_buf* a, nb200_real value)
 {
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fill: a is not a buffer of this context"); }
 	if(a->lane_elems == 0) { return NB200_OK; }
+	step_op op = make_op(SOP_FILL, a);
+	op.coef.push_back(value);
+	STEP_NOTE(ctx, op);
+	return fill_lanes(ctx, a, value);
+}
+
+namespace {
+int fill_lanes(nb200_ctx* ctx, nb200_buf* a, real value)
+{
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];
@@ -674,6 +1074,7 @@ NB200_API int nb200_fill(nb200_ctx* ctx, nb200_buf* a, nb200_real value)
 	}
 	return NB200_OK;
 }
+}  // namespace
 
 // ---- direct all-pairs --------------------------------------------------------------
 namespace {
@@ -842,6 +1243,7 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	int rc = check_state_pair(ctx, y, f, "fcompute_direct");
 	if(rc != NB200_OK) { return rc; }
 	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_direct: y and f must differ"); }
+	STEP_NOTE(ctx, make_op(SOP_FCOMPUTE_DIRECT, y, f));
 	rc = pack_and_gather(ctx, y);
 	if(rc != NB200_OK) { return rc; }
 	if(const int edge = sym_tile_edge(ctx))
@@ -938,6 +1340,7 @@ NB200_API int nb200_bh_configure(nb200_ctx* ctx, nb200_real ratio, int layout, s
 	{
 		return fail(ctx, NB200_ERR_ARG, "bh_configure: tree_layout must be heap or heap_stackless");
 	}
+	step_invalidate(ctx);
 	ctx->bh_ratio = ratio;
 	ctx->bh_layout = layout;
 	ctx->bh_build_rate = tree_build_rate;
@@ -952,6 +1355,11 @@ NB200_API int nb200_fcompute_bh(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f
 	if((ctx->n & (ctx->n - 1)) != 0)
 	{
 		return fail(ctx, NB200_ERR_UNSUPPORTED, "fcompute_bh: N = %zu is not a power of two (kd-heap leaves are [N, 2N))", ctx->n);
+	}
+	{
+		step_op op = make_op(SOP_FCOMPUTE_BH, y, f);
+		op.step = ctx->bh_build_rate == 0 ? 0 : step;	// the step number only matters when the tree is kept for several steps
+		STEP_NOTE(ctx, op);
 	}
 	rc = pack_and_gather(ctx, y);
 	if(rc != NB200_OK) { return rc; }
@@ -988,6 +1396,7 @@ NB200_API int nb200_bh_export_tree(nb200_ctx* ctx, int lane, nb200_real* xyzr, n
 {
 	if(ctx == nullptr || lane < 0 || static_cast<size_t>(lane) >= ctx->lanes.size()) { return NB200_ERR_ARG; }
 	nb200_lane& l = ctx->lanes[static_cast<size_t>(lane)];
+	step_break(ctx);
 	if(l.bh == nullptr) { return fail(ctx, NB200_ERR_STATE, "bh_export_tree: no tree has been built"); }
 	CU(ctx, cudaSetDevice(l.dev));
 	std::string err;
@@ -999,6 +1408,7 @@ NB200_API int nb200_bh_export_tree(nb200_ctx* ctx, int lane, nb200_real* xyzr, n
 NB200_API int nb200_bh_walk_stats(nb200_ctx* ctx, int enable, unsigned long long* visits, unsigned long long* interactions)
 {
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	step_invalidate(ctx);
 	unsigned long long v = 0, k = 0;
 	if(ctx->bh_stats)
 	{
@@ -1025,6 +1435,11 @@ NB200_API int nb200_fmadd_inplace(nb200_ctx* ctx, nb200_buf* a, const nb200_buf*
 	if(!valid(ctx, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: b is not a buffer of this context"); }
 	if(!same_shape(a, b)) { return fail(ctx, NB200_ERR_ARG, "fmadd_inplace: size does not match"); }
 	if(a->lane_elems == 0) { return NB200_OK; }
+	{
+		step_op op = make_op(SOP_FMADD_INPLACE, a, b);
+		op.coef.push_back(c);
+		STEP_NOTE(ctx, op);
+	}
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];
@@ -1043,6 +1458,11 @@ NB200_API int nb200_fmadd(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, cons
 	if(!valid(ctx, c)) { return fail(ctx, NB200_ERR_ARG, "fmadd: c is not a buffer of this context"); }
 	if(!same_shape(a, b) || !same_shape(a, c)) { return fail(ctx, NB200_ERR_ARG, "fmadd: size does not match"); }
 	if(a->lane_elems == 0) { return NB200_OK; }
+	{
+		step_op op = make_op(SOP_FMADD, a, b, c);
+		op.coef.push_back(d);
+		STEP_NOTE(ctx, op);
+	}
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];
@@ -1057,7 +1477,7 @@ namespace {
 // Shared body of fmaddn / fmaddn_inplace / fmaddn_corr.
 //   base: starting value (NULL = zeros); for the in-place forms base == a.
 //   corr: non-NULL selects the Kahan kernel.
-int fused_terms(nb200_ctx* ctx, const char* who, nb200_buf* a, const nb200_buf* base, nb200_buf* corr,
+int fused_terms(nb200_ctx* ctx, const char* who, int kind, nb200_buf* a, const nb200_buf* base, nb200_buf* corr,
 				const nb200_buf* const* terms, const nb200_real* coeff, size_t n, bool keep_a_if_no_terms)
 {
 	// Collect non-zero terms first: zero coefficients are skipped before their buffers are even looked at
@@ -1079,6 +1499,16 @@ int fused_terms(nb200_ctx* ctx, const char* who, nb200_buf* a, const nb200_buf* 
 		return nb200_fill(ctx, a, 0);				// fmaddn with b == NULL: a = 0
 	}
 	if(a->lane_elems == 0) { return NB200_OK; }
+	{
+		// recorded with the zero-coefficient terms already dropped: re-issuing it gives the same launches
+		step_op op = make_op(kind, a, kind == SOP_FMADDN_CORR ? corr : (kind == SOP_FMADDN ? base : nullptr));
+		for(size_t k : used)
+		{
+			op.list.push_back(terms[k]);
+			op.coef.push_back(coeff[k]);
+		}
+		STEP_NOTE(ctx, op);
+	}
 	for(size_t first = 0; first < used.size(); first += NB200_MAX_TERMS)
 	{
 		size_t cnt = std::min<size_t>(NB200_MAX_TERMS, used.size() - first);
@@ -1115,7 +1545,7 @@ NB200_API int nb200_fmaddn_inplace(nb200_ctx* ctx, nb200_buf* a, const nb200_buf
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(c == nullptr) { return fail(ctx, NB200_ERR_ARG, "fmaddn_inplace: c == NULL"); }
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaddn_inplace: a is not a buffer of this context"); }
-	return fused_terms(ctx, "fmaddn_inplace", a, a, nullptr, b, c, n, true);
+	return fused_terms(ctx, "fmaddn_inplace", SOP_FMADDN_INPLACE, a, a, nullptr, b, c, n, true);
 }
 
 NB200_API int nb200_fmaddn(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, const nb200_buf* const* c, const nb200_real* d, size_t n)
@@ -1129,7 +1559,7 @@ NB200_API int nb200_fmaddn(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b, con
 		if(!same_shape(a, b)) { return fail(ctx, NB200_ERR_ARG, "fmaddn: size does not match"); }
 	}
 	// Reference quirk kept: with b != NULL and no non-zero term, a is NOT assigned (nbody_engine.cpp:87-112).
-	return fused_terms(ctx, "fmaddn", a, b, nullptr, c, d, n, b != nullptr);
+	return fused_terms(ctx, "fmaddn", SOP_FMADDN, a, b, nullptr, c, d, n, b != nullptr);
 }
 
 NB200_API int nb200_fmaddn_corr(nb200_ctx* ctx, nb200_buf* a, nb200_buf* corr, const nb200_buf* const* b, const nb200_real* c, size_t n)
@@ -1145,13 +1575,17 @@ NB200_API int nb200_fmaddn_corr(nb200_ctx* ctx, nb200_buf* a, nb200_buf* corr, c
 	{
 		if(b == nullptr || !valid(ctx, b[k])) { return fail(ctx, NB200_ERR_ARG, "fmaddn_corr: b[%zu] is not a buffer of this context", k); }
 	}
-	return fused_terms(ctx, "fmaddn_corr", a, a, corr, b, c, n, true);
+	return fused_terms(ctx, "fmaddn_corr", SOP_FMADDN_CORR, a, a, corr, b, c, n, true);
 }
 
 NB200_API int nb200_fmaxabs(nb200_ctx* ctx, const nb200_buf* a, nb200_real* result)
 {
 	if(ctx == nullptr || result == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, a)) { return fail(ctx, NB200_ERR_ARG, "fmaxabs: a is not a buffer of this context"); }
+	{
+		int rc = step_border(ctx, make_op(SOP_FMAXABS, a));
+		if(rc != NB200_OK) { return rc; }
+	}
 	if(a->lane_elems == 0)
 	{
 		*result = 0;
@@ -1195,6 +1629,11 @@ NB200_API int nb200_clamp(nb200_ctx* ctx, nb200_buf* y, nb200_real b)
 	if(ctx == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "clamp: y is not a buffer of this context"); }
 	if(!y->sharded) { return fail(ctx, NB200_ERR_ARG, "clamp: y must be a state vector of 6*N elements"); }
+	{
+		step_op op = make_op(SOP_CLAMP, y);
+		op.coef.push_back(b);
+		STEP_NOTE(ctx, op);
+	}
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];
@@ -1212,6 +1651,7 @@ NB200_API int nb200_statistics(nb200_ctx* ctx, const nb200_buf* y, int with_ener
 	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
 	if(!valid(ctx, y)) { return fail(ctx, NB200_ERR_ARG, "statistics: y is not a buffer of this context"); }
 	if(ctx->n == 0 || !y->sharded) { return fail(ctx, NB200_ERR_ARG, "statistics: y must be a state vector of 6*N elements"); }
+	step_break(ctx);
 	if(with_energy)
 	{
 		int rc = pack_and_gather(ctx, y);	// the potential needs every body's position on every shard
@@ -1282,6 +1722,81 @@ NB200_API int nb200_statistics(nb200_ctx* ctx, const nb200_buf* y, int with_ener
 	return NB200_OK;
 }
 
+// ---- solver steps as CUDA graphs ------------------------------------------------------------------
+NB200_API int nb200_step_boundary(nb200_ctx* ctx)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	step_graph& sg = *ctx->sg;
+	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
+	int rc = NB200_OK;
+	if(sg.mode == SG_REPLAY)
+	{
+		if(sg.pos == 0) { return NB200_OK; }	// no calls since the last boundary
+		if(sg.pos == sg.seq.size())
+		{
+			if(sg.execs[sg.seg] != nullptr)
+			{
+				nb200_lane& l = ctx->lanes[0];
+				CU(ctx, cudaSetDevice(l.dev));
+				CU(ctx, cudaGraphLaunch(sg.execs[sg.seg], l.stream));
+				ctx->launches += sg.seg_launches[sg.seg];
+				++sg.graph_launches;
+			}
+			sg.pos = sg.seg = sg.seg_start = 0;
+			return NB200_OK;
+		}
+		rc = step_bail(ctx);	// the step ended before the recorded one did
+		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+	}
+	if(sg.mode == SG_CAPTURE)
+	{
+		if(sg.cur.empty()) { return NB200_OK; }
+		rc = step_close_segment(ctx);	// the last segment of the step
+		if(sg.mode == SG_OFF) { return rc; }
+		bool same = sg.cur.size() == sg.seq.size();
+		for(size_t k = 0; same && k < sg.cur.size(); ++k) { same = sg.cur[k].same(sg.seq[k]); }
+		if(same)
+		{
+			sg.mode = SG_REPLAY;
+			sg.pos = sg.seg = sg.seg_start = 0;
+			sg.launches_per_step = 0;
+			for(unsigned long long c : sg.seg_launches) { sg.launches_per_step += c; }
+		}
+		else
+		{
+			step_drop_graphs(ctx);
+			sg.seq.swap(sg.cur);	// a clean step all the same: try the next one against it
+			step_failure(ctx);
+		}
+		sg.cur.clear();
+		sg.clean = true;
+		return rc;
+	}
+	// SG_RECORD: a clean step (nothing host-visible inside except segment borders) becomes the candidate
+	if(sg.clean && !sg.cur.empty())
+	{
+		sg.seq.swap(sg.cur);
+		sg.mode = SG_CAPTURE;
+	}
+	else
+	{
+		sg.seq.clear();
+	}
+	sg.cur.clear();
+	sg.clean = true;
+	return rc;
+}
+
+NB200_API int nb200_step_graph_stats(const nb200_ctx* ctx, unsigned long long out[4])
+{
+	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
+	out[0] = ctx->sg->graph_launches;
+	out[1] = ctx->sg->bailouts;
+	out[2] = static_cast<unsigned long long>(ctx->sg->mode);
+	out[3] = ctx->sg->launches_per_step;
+	return NB200_OK;
+}
+
 // ---- instrumentation ---------------------------------------------------------------------------
 NB200_API unsigned long long nb200_launch_count(const nb200_ctx* ctx)
 {
@@ -1291,6 +1806,7 @@ NB200_API unsigned long long nb200_launch_count(const nb200_ctx* ctx)
 NB200_API int nb200_last_fcompute_ms(nb200_ctx* ctx, float out[4])
 {
 	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
+	step_break(ctx);
 	nb200_lane& l = ctx->lanes[0];
 	CU(ctx, cudaSetDevice(l.dev));
 	CU(ctx, cudaStreamSynchronize(l.stream));
@@ -1314,6 +1830,7 @@ NB200_API int nb200_last_direct_path(const nb200_ctx* ctx)
 NB200_API int nb200_mark(nb200_ctx* ctx, int slot)
 {
 	if(ctx == nullptr || slot < 0 || slot >= 8) { return NB200_ERR_ARG; }
+	step_break(ctx);	// a mark inside a deferred step would time nothing
 	nb200_lane& l = ctx->lanes[0];
 	CU(ctx, cudaSetDevice(l.dev));
 	CU(ctx, cudaEventRecord(l.ev_mark[slot], l.stream));
@@ -1333,6 +1850,7 @@ NB200_API int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms
 NB200_API int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s)
 {
 	if(ctx == nullptr || fma_lane_per_s == nullptr) { return NB200_ERR_ARG; }
+	step_break(ctx);
 	nb200_lane& l = ctx->lanes[0];
 	CU(ctx, cudaSetDevice(l.dev));
 	cudaEvent_t e0, e1;
@@ -1370,7 +1888,20 @@ NB200_API int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_p
 NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value)
 {
 	if(ctx == nullptr || name == nullptr) { return NB200_ERR_ARG; }
-	if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
+	step_invalidate(ctx);	// a recorded step was launched with the old settings
+	if(strcmp(name, "step_graph") == 0)
+	{
+		// deferral needs one stream that sees every call: single-shard contexts only (accepted and ignored otherwise)
+		const bool can = ctx->lanes.size() == 1 && ctx->nranks == 1;
+		step_graph& sg = *ctx->sg;
+		sg.seq.clear();
+		sg.cur.clear();
+		sg.clean = true;
+		sg.pos = 0;
+		sg.failures = 0;
+		sg.mode = (value != 0 && can) ? SG_RECORD : SG_OFF;
+	}
+	else if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
 	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = warp-coherent, 1 = one thread per target
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }

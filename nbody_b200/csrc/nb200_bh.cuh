@@ -520,6 +520,96 @@ __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const no
 	}
 }
 
+// TPL targets per lane: one warp walks the union of 32 * TPL consecutive leaves, so the node load, the index algebra,
+// the votes and the loop control of a visit are shared by TPL acceptance tests per lane instead of one. Each target
+// still accepts exactly the nodes of its own stackless traversal, in the same order: results are bit-identical to
+// bh_walk_warp (tested). Target k of lane l is leaf base + 32 k + l, so every load and store stays coalesced.
+template<int TPL, bool STATS>
+__global__ void __launch_bounds__(128, TPL == 2 ? 8 : 4) bh_walk_warp_multi(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+														 const int* __restrict__ body_n, real* __restrict__ acc_leaf, int3 deal,
+														 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
+														 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
+{
+	const int	warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int	lane = threadIdx.x & 31;
+	const int	tree_size = 2 * n;
+	int			t[TPL], leaf[TPL], resume[TPL];
+	bool		awake[TPL];
+	real		px[TPL], py[TPL], pz[TPL], ax[TPL], ay[TPL], az[TPL];
+	unsigned	visits = 0, inter = 0;
+#pragma unroll
+	for(int k = 0; k < TPL; ++k)
+	{
+		t[k] = warp * (32 * TPL) + 32 * k + lane;
+		const int tc = t[k] < n_targets ? t[k] : n_targets - 1;	// idle slots shadow the last target and never store
+		leaf[k] = n + ((tc / deal.x) * deal.y + deal.z) * deal.x + tc % deal.x;
+		const node4 me = load_node(xyzr, leaf[k]);
+		px[k] = me.x; py[k] = me.y; pz[k] = me.z;
+		ax[k] = ay[k] = az[k] = 0;
+		resume[k] = 1;
+		awake[k] = true;
+	}
+	int curr = 1;	// warp-uniform
+	do
+	{
+		const node4	nd = load_node(xyzr, curr);
+		const int	skip = heap_skip_idx(curr);
+		const int	child = curr << 1;
+		real		dx[TPL], dy[TPL], dz[TPL], d2[TPL];
+		bool		accept[TPL];
+		bool		any_accept = false, any_open = false;
+#pragma unroll
+		for(int k = 0; k < TPL; ++k)
+		{
+			awake[k] = awake[k] || (curr == resume[k]);
+			dx[k] = px[k] - nd.x; dy[k] = py[k] - nd.y; dz[k] = pz[k] - nd.z;
+			d2[k] = dx[k] * dx[k] + dy[k] * dy[k] + dz[k] * dz[k];	// same expression as bh_walk_warp (see the note there)
+			accept[k] = awake[k] && (d2[k] > nd.w);
+			any_accept = any_accept || accept[k];
+			any_open = any_open || (awake[k] && !accept[k]);
+			if(STATS) { visits += (awake[k] && t[k] < n_targets) ? 1u : 0u; }
+		}
+		if(__any_sync(0xffffffffu, any_accept))
+		{
+			const real m = nmass[curr];
+#pragma unroll
+			for(int k = 0; k < TPL; ++k)
+			{
+				if(accept[k])
+				{
+					node_force_from_test(dx[k], dy[k], dz[k], d2[k], m, ax[k], ay[k], az[k]);
+					if(STATS && t[k] < n_targets) { ++inter; }
+					awake[k] = false;
+					resume[k] = skip;
+				}
+			}
+		}
+		curr = (__any_sync(0xffffffffu, any_open) && child < tree_size) ? child : skip;
+	} while(curr != 1);
+#pragma unroll
+	for(int k = 0; k < TPL; ++k)
+	{
+		if(t[k] < n_targets)
+		{
+			if(acc_leaf != nullptr)
+			{
+				acc_leaf[t[k]] = ax[k];
+				acc_leaf[n_shard + t[k]] = ay[k];
+				acc_leaf[2 * n_shard + t[k]] = az[k];
+			}
+			else
+			{
+				store_f(y, f, n_shard, static_cast<size_t>(body_n[leaf[k]] - shard_first), ax[k], ay[k], az[k]);
+			}
+		}
+	}
+	if(STATS && (visits | inter) != 0)
+	{
+		atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
+		atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
+	}
+}
+
 // ---- host orchestration ----------------------------------------------------------------------------------------------
 #define BH_CU(call)                                                                                    \
 	do                                                                                                 \
@@ -694,6 +784,16 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	if(ctx->opt_walk_mode == 1)
 	{
 		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+	}
+	else if(ctx->opt_walk_mode == 2 || ctx->opt_walk_mode == 4)
+	{
+		// several targets per lane (a deal chunk is a multiple of 128 leaves or the whole shard, so a warp's leaves stay consecutive)
+		const int		tpl = static_cast<int>(ctx->opt_walk_mode);
+		const unsigned	mgrid = static_cast<unsigned>((n_targets + 128 * tpl - 1) / (128 * tpl));
+		if(tpl == 2 && stats != nullptr) { bh_walk_warp_multi<2, true><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		else if(tpl == 2) { bh_walk_warp_multi<2, false><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		else if(stats != nullptr) { bh_walk_warp_multi<4, true><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		else { bh_walk_warp_multi<4, false><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
 	}
 	else if(stats != nullptr)
 	{

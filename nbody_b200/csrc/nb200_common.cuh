@@ -68,6 +68,7 @@ struct nb200_lane
 };
 
 struct nccl_api;
+struct step_graph;
 
 struct nb200_ctx
 {
@@ -87,6 +88,7 @@ struct nb200_ctx
 	int			last_direct_path = 0;
 	bool		peer_loads = true;	// every lane can load from every other lane's memory (same device or peer access enabled)
 	std::string	err;
+	step_graph*	sg = nullptr;	// solver steps as CUDA graphs (nb200_stepgraph.cuh)
 	// Barnes-Hut configuration
 	real		bh_ratio = 10;
 	int			bh_layout = NB200_TREE_HEAP_STACKLESS;

@@ -239,6 +239,27 @@ __global__ void __launch_bounds__(NB200_EW_THREADS) ew_clamp(real* y, real b, si
 	y[i] = v;
 }
 
+// Body arrays <-> state shard. aos = [pos: n_shard x 3 | vel: n_shard x 3] (two nbvertex_t arrays back to back),
+// y = 6 rows of n_shard. Both run flat over the 6 n_shard elements of the side they WRITE, so stores are fully
+// coalesced and the strided side is served from L1/L2 sectors that neighbouring threads share.
+__global__ void __launch_bounds__(NB200_EW_THREADS) ew_state_to_bodies(const real* __restrict__ y, real* __restrict__ aos, size_t n_shard)
+{
+	const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(e >= 6 * n_shard) { return; }
+	const size_t half = e / (3 * n_shard);	// 0 = positions, 1 = velocities
+	const size_t r = e - half * 3 * n_shard;
+	aos[e] = y[(3 * half + r % 3) * n_shard + r / 3];
+}
+
+__global__ void __launch_bounds__(NB200_EW_THREADS) ew_bodies_to_state(const real* __restrict__ aos, real* __restrict__ y, size_t n_shard)
+{
+	const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if(e >= 6 * n_shard) { return; }
+	const size_t row = e / n_shard;
+	const size_t i = e - row * n_shard;
+	y[e] = aos[(row / 3) * 3 * n_shard + 3 * i + row % 3];
+}
+
 // FMA-pipe peak probe: 8 independent chains per thread, `iters` x 8 FMAs each.
 __global__ void __launch_bounds__(256) probe_fma(real* out, int iters, real seed)
 {

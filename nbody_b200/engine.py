@@ -81,6 +81,12 @@ def load_library(precision="f64"):
     sig("nb200_fmaxabs", i32, vp, vp, P(real))
     sig("nb200_clamp", i32, vp, vp, real)
     sig("nb200_statistics", i32, vp, vp, i32, P(C.c_double))
+    sig("nb200_write_bodies", i32, vp, vp, vp, vp)
+    sig("nb200_read_bodies", i32, vp, vp, vp, vp)
+    sig("nb200_host_register", i32, vp, vp, sz)
+    sig("nb200_host_unregister", i32, vp, vp)
+    sig("nb200_step_boundary", i32, vp)
+    sig("nb200_step_graph_stats", i32, vp, P(ull))
     sig("nb200_launch_count", ull, vp)
     sig("nb200_last_fcompute_ms", i32, vp, P(C.c_float))
     sig("nb200_last_direct_path", i32, vp)
@@ -249,6 +255,49 @@ class Engine:
         """Host copy of the current state vector (``get_data`` without the AoS transpose)."""
         return self.read_buffer(self._y)
 
+    def init_bodies(self, pos, vel, mass):
+        """``init(nbody_data*)`` from the AoS body arrays themselves: pos, vel are N x 3 (``nbody_data::get_vertites()``
+        / ``get_velosites()``); the transpose to [rx|ry|rz|vx|vy|vz] happens on the device (``nb200_write_bodies``)."""
+        mass = np.ascontiguousarray(mass, dtype=self.dtype)
+        pos = np.ascontiguousarray(pos, dtype=self.dtype)
+        vel = np.ascontiguousarray(vel, dtype=self.dtype)
+        if mass.size == 0 or pos.shape != (mass.size, 3) or vel.shape != (mass.size, 3):
+            log.error("init_bodies: pos and vel must be N x 3")
+            return False
+        if self._check(self.lib.nb200_set_bodies(self.ctx, mass.size, mass.ctypes.data_as(C.c_void_p)), "init") != 0:
+            return False
+        self._n = mass.size
+        self._y = self.create_buffer(6 * mass.size * self.dtype.itemsize)
+        if self._y is None:
+            return False
+        return self._check(self.lib.nb200_write_bodies(self.ctx, self._y.handle, pos.ctypes.data_as(C.c_void_p),
+                                                       vel.ctypes.data_as(C.c_void_p)), "init_bodies") == 0
+
+    def get_bodies(self, pos=None, vel=None, y=None):
+        """``get_data(nbody_data*)``: the state vector back as AoS body arrays (N x 3 each), transposed on the device
+        and copied shard by shard straight into ``pos`` / ``vel`` (pin them once with ``host_register``)."""
+        y = self._y if y is None else y
+        h = self._h(y, "get_bodies", "y")
+        if h is None:
+            return None
+        pos = np.empty((self._n, 3), dtype=self.dtype) if pos is None else pos
+        vel = np.empty((self._n, 3), dtype=self.dtype) if vel is None else vel
+        for a in (pos, vel):
+            if a.dtype != self.dtype or a.shape != (self._n, 3) or not a.flags.c_contiguous:
+                log.warning("get_bodies: destination must be a contiguous N x 3 array of the engine's dtype")
+                return None
+        if self._check(self.lib.nb200_read_bodies(self.ctx, h, pos.ctypes.data_as(C.c_void_p),
+                                                  vel.ctypes.data_as(C.c_void_p)), "get_bodies") != 0:
+            return None
+        return pos, vel
+
+    def host_register(self, array):
+        return self._check(self.lib.nb200_host_register(self.ctx, array.ctypes.data_as(C.c_void_p), array.nbytes),
+                           "host_register")
+
+    def host_unregister(self, array):
+        return self.lib.nb200_host_unregister(self.ctx, array.ctypes.data_as(C.c_void_p))
+
     def problem_size(self):
         return 6 * self._n
 
@@ -256,8 +305,16 @@ class Engine:
         return self._y
 
     def advise_time(self, dt):
+        """End of a solver step; also the boundary the library's step graphs are cut at (``step_graph`` option)."""
         self._time += dt
         self._step += 1
+        self._check(self.lib.nb200_step_boundary(self.ctx), "step_boundary")
+
+    def step_graph_stats(self):
+        out = (C.c_ulonglong * 4)()
+        self.lib.nb200_step_graph_stats(self.ctx, out)
+        return dict(graph_launches=int(out[0]), bailouts=int(out[1]),
+                    state=("off", "record", "capture", "replay")[int(out[2])], launches_per_step=int(out[3]))
 
     def get_time(self):
         return self._time

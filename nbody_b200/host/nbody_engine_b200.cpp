@@ -6,6 +6,7 @@
 #include "nb200.h"
 
 static_assert(sizeof(nb200_real) == sizeof(nbcoord_t), "libnb200 precision must match NB_COORD_PRECISION");
+static_assert(sizeof(nbvertex_t) == 3 * sizeof(nbcoord_t), "nbvertex_t must be three packed coordinates");
 
 class nbody_engine_b200::smemory : public nbody_engine::memory
 {
@@ -52,9 +53,40 @@ struct nbody_engine_b200::data
 	nb200_ctx*			m_ctx;
 	smemory*			m_y;
 	nbody_data*			m_data;
+	bool				m_step_graph;
+	void*				m_pinned[2];
 	data() : m_force(ef_direct), m_ratio(10), m_tree_build_rate(0), m_tree_layout(etl_heap_stackless),
-		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr)
+		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr), m_step_graph(false)
 	{
+		m_pinned[0] = m_pinned[1] = nullptr;
+	}
+	//! nbody_data's body arrays are pinned for as long as this engine serves them: get_data becomes two DMA copies
+	void pin(nbody_data* body_data)
+	{
+		unpin();
+		if(m_ctx == nullptr || body_data == nullptr)
+		{
+			return;
+		}
+		void*	arr[2] = {body_data->get_vertites(), body_data->get_velosites()};
+		for(int i = 0; i != 2; ++i)
+		{
+			if(nb200_host_register(m_ctx, arr[i], body_data->get_count() * sizeof(nbvertex_t)) == NB200_OK)
+			{
+				m_pinned[i] = arr[i];
+			}
+		}
+	}
+	void unpin()
+	{
+		for(int i = 0; i != 2; ++i)
+		{
+			if(m_pinned[i] != nullptr && m_ctx != nullptr)
+			{
+				nb200_host_unregister(m_ctx, m_pinned[i]);
+			}
+			m_pinned[i] = nullptr;
+		}
 	}
 	//! memory -> C-ABI handle; NULL (after logging) for foreign or NULL memory, like the reference's dynamic_cast checks
 	nb200_buf* handle(const memory* m, const char* name) const
@@ -89,6 +121,7 @@ nbody_engine_b200::nbody_engine_b200(e_force force, nbcoord_t distance_to_node_r
 nbody_engine_b200::~nbody_engine_b200()
 {
 	delete d->m_y;
+	d->unpin();
 	nb200_destroy(d->m_ctx);
 	delete d;
 }
@@ -116,6 +149,10 @@ bool nbody_engine_b200::ensure_context()
 		int layout = (d->m_tree_layout == etl_heap) ? NB200_TREE_HEAP : NB200_TREE_HEAP_STACKLESS;
 		d->check(nb200_bh_configure(d->m_ctx, d->m_ratio, layout, d->m_tree_build_rate), "nb200_bh_configure");
 	}
+	if(d->m_step_graph)
+	{
+		d->check(nb200_set_option(d->m_ctx, "step_graph", 1), "step_graph");
+	}
 	return true;
 }
 
@@ -138,21 +175,12 @@ bool nbody_engine_b200::init(nbody_data* body_data)
 	{
 		return false;
 	}
-	// AoS nbody_data -> [rx|ry|rz|vx|vy|vz] (nbody_engine_cuda.cpp:113-139)
-	std::vector<nbcoord_t>	ytmp(problem_size());
-	const nbvertex_t*		vrt = body_data->get_vertites();
-	const nbvertex_t*		vel = body_data->get_velosites();
-	for(size_t i = 0; i != count; ++i)
-	{
-		ytmp[i] = vrt[i].x;
-		ytmp[count + i] = vrt[i].y;
-		ytmp[2 * count + i] = vrt[i].z;
-		ytmp[3 * count + i] = vel[i].x;
-		ytmp[4 * count + i] = vel[i].y;
-		ytmp[5 * count + i] = vel[i].z;
-	}
-	write_buffer(d->m_y, ytmp.data());
-	return true;
+	// AoS nbody_data -> [rx|ry|rz|vx|vy|vz] (nbody_engine_cuda.cpp:113-139 does this in a host loop): the body arrays
+	// go to the device as they are and are transposed there
+	d->pin(body_data);
+	int rc = nb200_write_bodies(d->m_ctx, d->m_y->buf(), &body_data->get_vertites()->x, &body_data->get_velosites()->x);
+	d->check(rc, "init");
+	return rc == NB200_OK;
 }
 
 void nbody_engine_b200::get_data(nbody_data* body_data)
@@ -161,20 +189,14 @@ void nbody_engine_b200::get_data(nbody_data* body_data)
 	{
 		return;
 	}
-	size_t					count = body_data->get_count();
-	std::vector<nbcoord_t>	ytmp(problem_size());
-	read_buffer(ytmp.data(), d->m_y);
-	nbvertex_t*				vrt = body_data->get_vertites();
-	nbvertex_t*				vel = body_data->get_velosites();
-	for(size_t i = 0; i != count; ++i)
+	if(6 * body_data->get_count() != problem_size())
 	{
-		vrt[i].x = ytmp[i];
-		vrt[i].y = ytmp[count + i];
-		vrt[i].z = ytmp[2 * count + i];
-		vel[i].x = ytmp[3 * count + i];
-		vel[i].y = ytmp[4 * count + i];
-		vel[i].z = ytmp[5 * count + i];
+		qDebug() << "get_data: body count does not match the engine's";
+		return;
 	}
+	// device-side transpose + two DMA copies per shard straight into nbody_data's arrays
+	// (the reference: full-buffer D2H + host loop, nbody_engine_cuda.cpp:141-175)
+	d->check(nb200_read_bodies(d->m_ctx, d->m_y->buf(), &body_data->get_vertites()->x, &body_data->get_velosites()->x), "get_data");
 }
 
 size_t nbody_engine_b200::problem_size() const
@@ -191,6 +213,8 @@ nbody_engine::memory* nbody_engine_b200::get_y()
 void nbody_engine_b200::advise_time(const nbcoord_t& dt)
 {
 	d->m_data->advise_time(dt);
+	// every solver ends its step here: the boundary nb200's step graphs are cut at (no-op unless step_graph=1)
+	nb200_step_boundary(d->m_ctx);
 }
 
 nbcoord_t nbody_engine_b200::get_time() const
@@ -528,6 +552,20 @@ void nbody_engine_b200::set_use_nccl(bool active)
 	Q_UNUSED(active);
 }
 
+void nbody_engine_b200::set_step_graph(bool active)
+{
+	d->m_step_graph = active;
+	if(d->m_ctx != nullptr)
+	{
+		d->check(nb200_set_option(d->m_ctx, "step_graph", active ? 1 : 0), "step_graph");
+	}
+}
+
+bool nbody_engine_b200::step_graph_stats(unsigned long long out[4]) const
+{
+	return d->m_ctx != nullptr && nb200_step_graph_stats(d->m_ctx, out) == NB200_OK;
+}
+
 bool nbody_engine_b200::statistics(const memory* _y, bool with_energy, double out[11])
 {
 	nb200_buf*	y = d->handle(_y, "y");
@@ -586,6 +624,7 @@ nbody_engine* nbody_create_engine_b200(const QVariantMap& param)
 	}
 	engine->set_block_size(param.value("block_size", NBODY_DATA_BLOCK_SIZE).toInt());
 	engine->set_use_nccl(param.value("use_nccl", false).toBool());
+	engine->set_step_graph(param.value("step_graph", false).toBool());
 	return engine;
 }
 
@@ -618,4 +657,10 @@ extern "C" __attribute__((visibility("default"))) void nbody_engine_b200_synchro
 	{
 		e->synchronize();
 	}
+}
+
+extern "C" __attribute__((visibility("default"))) int nbody_engine_b200_step_graph_stats(void* engine, unsigned long long out[4])
+{
+	nbody_engine_b200* e = dynamic_cast<nbody_engine_b200*>(static_cast<nbody_engine*>(engine));
+	return (e != nullptr && e->step_graph_stats(out)) ? 0 : -1;
 }

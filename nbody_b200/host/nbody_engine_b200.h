@@ -66,6 +66,11 @@ public:
 	void set_block_size(int block_size);
 	//! Single-process lanes exchange shards by peer copies; NCCL is used by the one-process-per-GPU mode only
 	void set_use_nccl(bool);
+	//! Solver steps as CUDA graphs (factory parameter step_graph=1): a step that repeats the previous one call for call
+	//! is replayed as one cudaGraphLaunch from advise_time(); results are those of the eager engine (include/nb200.h)
+	void set_step_graph(bool);
+	//! {graphs launched, replays abandoned, state, kernels per replayed step}
+	bool step_graph_stats(unsigned long long out[4]) const;
 	//! Device-side conservation sums of nbody_data::print_statistics (nbody_data.cpp:57-103) for a state vector:
 	//! out = {P[3], L[3], Ekin, Epot, mass centre[3]}; Epot (O(N^2), on the GPU) only when with_energy. False on error.
 	bool statistics(const memory* y, bool with_energy, double out[11]);

@@ -67,6 +67,25 @@ def test_bh_walk_modes_bit_identical():
     assert sa == sb and sa[0] > sa[1] > 0
 
 
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("n,ratio,devices", [(2, 10.0, "0"), (64, 10.0, "0"), (2048, 10.0, "0"), (2048, 1.0, "0,0"),
+                                             (65536, 10.0, "0"), (65536, 2.0, "0,0,0,0")])
+def test_bh_several_targets_per_lane_bit_identical(precision, n, ratio, devices):
+    """walk_mode 2 / 4: one warp walks the union of 64 / 128 consecutive leaves (2 / 4 targets per lane); every target
+    still accepts exactly the nodes of its own stackless traversal, so forces and visit counts equal walk_mode 0."""
+    y, m = universe(n, precision) if n >= 64 else (None, None)
+    if y is None:
+        g = load_golden_npz("g1_n128", precision)
+        idx = np.arange(n)
+        y = np.concatenate([g["y"][r * 128 + idx] for r in range(6)])
+        m = g["mass"][idx]
+    (a,), _, sa = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=0, stats=True)
+    for mode in (2, 4):
+        (b,), _, sb = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=mode, stats=True)
+        assert np.array_equal(a, b), "walk_mode %d" % mode
+        assert sa == sb
+
+
 def test_bh_counts_match_oracle(oracle64):
     g = load_golden_npz("g1_n2048")
     t = oracle64.heap_build(g["y"], g["mass"], 10.0)
