@@ -73,7 +73,7 @@ def test_bh_walk_modes_bit_identical():
 def test_bh_several_targets_per_lane_bit_identical(precision, n, ratio, devices):
     """walk_mode 2 / 4: one warp walks the union of 64 / 128 consecutive leaves (2 / 4 targets per lane); every target
     still accepts exactly the nodes of its own stackless traversal, so forces and visit counts equal walk_mode 0."""
-    y, m = universe(n, precision) if n >= 64 else (None, None)
+    y, m = universe(n, precision) if n >= 128 else (None, None)   # make_universe rounds up to 2 x 64 bodies
     if y is None:
         g = load_golden_npz("g1_n128", precision)
         idx = np.arange(n)
