@@ -360,16 +360,16 @@ def run_nb200(args):
             achieved = alg_bytes / world / (force_ms * 1e-3) / 1e9
             peak = hbm or 6650.0
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "kernel": "bh_walk_warp", "kernel_ms": force_ms, "phases_ms": phases,
+                        "kernel": "bh_walk_warp_multi<2> (two targets per lane)", "kernel_ms": force_ms, "phases_ms": phases,
                         "node_visits": visits, "interactions": inter, "algorithmic_bytes": alg_bytes,
                         "note": "algorithmic bytes count every per-target node visit; the warp-coherent walk loads each node once per warp "
                                 "and the upper tree stays in L1/L2, so the fraction can exceed 1 (SURVEY 8d says so); see profiles/ for DRAM bytes",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm else "fallback 6.65 TB/s (B200_PROFILING.md)"}
             if n == N_BH and world == 1 and args.ratio == 10.0 and precision == "f64":
-                # one ncu --set full capture of this exact launch (profiles/r1_ncu_bh_walk_n4m.csv):
-                # dram__bytes_read.sum 3.035 GB + dram__bytes_write.sum 0.804 GB per launch; L2 hit 98.5 %, L1 hit 38 %
-                roofline["traffic"] = 3.840e9
-                roofline["traffic_source"] = "profiles/r1_ncu_bh_walk_n4m.csv (bytes per launch)"
+                # one ncu --set full capture of this exact launch (profiles/r1_ncu_bh_walk_multi_n4m.csv):
+                # dram__bytes_read.sum 2.942 GB + dram__bytes_write.sum 0.784 GB per launch; L2 hit 96.5 %, L1 hit 56 %
+                roofline["traffic"] = 3.726e9
+                roofline["traffic_source"] = "profiles/r1_ncu_bh_walk_multi_n4m.csv (bytes per launch)"
             e2e_obj = None
             if e2e:
                 e2e_obj = {"value": e2e[0] * 1e3 / args.steps, "unit": unit, "h2d_bytes_per_step": e2e[1],

@@ -213,8 +213,8 @@ int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms);
 /* FP64/FP32 FMA-pipe peak probe: runs a dependent-chain-free FMA kernel for
  * ~`ms` milliseconds and returns achieved FMA instructions (per lane) per second. */
 int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s);
-/* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "walk_mode" (0 = warp-coherent walk,
- * 1 = one thread per target), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
+/* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "walk_mode" (0 = automatic: warp-coherent walk
+ * with two targets per lane; 1 = one thread per target; 2 / 4 = targets per lane; 32 = one target per lane), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
 int nb200_set_option(nb200_ctx* ctx, const char* name, long long value);
 
 #ifdef __cplusplus

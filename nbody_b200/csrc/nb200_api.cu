@@ -844,6 +844,7 @@ NB200_API size_t nb200_size(const nb200_buf* b)
 NB200_API int nb200_lane_ptr(nb200_ctx* ctx, nb200_buf* b, int lane, void** dptr, size_t* elems)
 {
 	if(!valid(ctx, b) || lane < 0 || static_cast<size_t>(lane) >= ctx->lanes.size()) { return NB200_ERR_ARG; }
+	step_invalidate(ctx);	// the caller may touch the memory behind the library's back: nothing may stay deferred
 	if(dptr) { *dptr = b->dptr[static_cast<size_t>(lane)]; }
 	if(elems) { *elems = b->lane_elems; }
 	return NB200_OK;
@@ -1093,7 +1094,7 @@ int sym_tile_edge(const nb200_ctx* ctx)
 		while(edge * 2 <= static_cast<long long>(ctx->n / 128) && edge < 8192) { edge *= 2; }
 	}
 	// 8 column blocks per phase round, 32*J bodies each; 32*I bodies per row block
-	const long long unit = ctx->opt_sym_shape == 3 ? 1024 : (ctx->opt_sym_shape >= 1 ? 512 : 256);
+	const long long unit = ctx->opt_sym_shape == 3 ? 1024 : (ctx->opt_sym_shape >= 1 ? 512 : 256);	// 6 = shape 1 with late shuffles
 	if(edge % unit != 0 || edge % 256 != 0 || edge > 8192) { return 0; }
 	return static_cast<int>(edge);
 }
@@ -1160,7 +1161,9 @@ int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
 #if NB200_PRECISION == 1
 		case 4: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<8>, mine, smem, T); break;	// packed f32x2
 		case 5: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<4>, mine, smem, T); break;
+		case 7: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<8, true>, mine, smem, T); break;	// all shuffles after the pairs (A/B)
 #endif
+		case 6: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2, false>, mine, smem, T); break;	// each column body shuffled right after its pairs (A/B: slower)
 		case 3: rc = sym_launch(ctx, l, direct_sym_tiles<4, 4>, mine, smem, T); break;
 		case 2: rc = sym_launch(ctx, l, direct_sym_tiles<8, 2>, mine, smem, T); break;
 		case 1: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2>, mine, smem, T); break;
@@ -1903,7 +1906,7 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	}
 	else if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
-	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = warp-coherent, 1 = one thread per target
+	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = automatic, 1 = thread per target, 2 / 4 = targets per lane, 32 = one per lane
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
 	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; }	// -1 auto, 0 off, 1 on
 	else if(strcmp(name, "direct_sym_tile") == 0) { ctx->opt_sym_tile = value; }

@@ -27,7 +27,9 @@
 //           node's skip_idx; every lane therefore accepts exactly the nodes, in exactly the
 //           order, of its own nbody_space_heap_stackless::traverse
 //           (nbody_space_heap_stackless.cpp:3-28) -- results are bit-identical to the
-//           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape).
+//           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape). By default each lane
+//           carries TWO targets (bh_walk_warp_multi<2>: the warp walks the union of 64 consecutive leaves), which
+//           shares the node load, index algebra, votes and loop control of a visit between two acceptance tests.
 //
 //   shards  with G shards (lanes or ranks) every shard builds the whole tree and walks chunks of 4096 CONSECUTIVE
 //           leaves dealt round-robin (a chunk is a compact region, so warps stay coherent; dealing evens out dense
@@ -524,8 +526,8 @@ __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const no
 // the votes and the loop control of a visit are shared by TPL acceptance tests per lane instead of one. Each target
 // still accepts exactly the nodes of its own stackless traversal, in the same order: results are bit-identical to
 // bh_walk_warp (tested). Target k of lane l is leaf base + 32 k + l, so every load and store stays coalesced.
-template<int TPL, bool STATS>
-__global__ void __launch_bounds__(128, TPL == 2 ? 8 : 4) bh_walk_warp_multi(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
+template<int TPL, bool STATS, int MINB>
+__global__ void __launch_bounds__(128, MINB) bh_walk_warp_multi(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 														 const int* __restrict__ body_n, real* __restrict__ acc_leaf, int3 deal,
 														 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
 														 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
@@ -785,15 +787,17 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	{
 		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
 	}
-	else if(ctx->opt_walk_mode == 2 || ctx->opt_walk_mode == 4)
+	else if(ctx->opt_walk_mode != 32)
 	{
-		// several targets per lane (a deal chunk is a multiple of 128 leaves or the whole shard, so a warp's leaves stay consecutive)
-		const int		tpl = static_cast<int>(ctx->opt_walk_mode);
+		// several targets per lane (a deal chunk is a multiple of 128 leaves or the whole shard, so a warp's leaves stay
+		// consecutive). Two is the measured optimum and the default: N = 4M, ratio 10 on one B200 -- FP64 675 -> 600 ms,
+		// FP32 647 -> 438 ms; four: 754 / 439 ms (114 registers, a quarter of the warp slots)
+		const int		tpl = ctx->opt_walk_mode == 4 ? 4 : 2;
 		const unsigned	mgrid = static_cast<unsigned>((n_targets + 128 * tpl - 1) / (128 * tpl));
-		if(tpl == 2 && stats != nullptr) { bh_walk_warp_multi<2, true><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
-		else if(tpl == 2) { bh_walk_warp_multi<2, false><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
-		else if(stats != nullptr) { bh_walk_warp_multi<4, true><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
-		else { bh_walk_warp_multi<4, false><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		if(tpl == 2 && stats != nullptr) { bh_walk_warp_multi<2, true, 8><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		else if(tpl == 2) { bh_walk_warp_multi<2, false, 8><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		else if(stats != nullptr) { bh_walk_warp_multi<4, true, 4><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		else { bh_walk_warp_multi<4, false, 4><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
 	}
 	else if(stats != nullptr)
 	{

@@ -87,7 +87,12 @@ __device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_r
 #ifndef NB200_SYM_MINB
 #define NB200_SYM_MINB 1
 #endif
-template<int I, int J>
+// LATE_SHUFFLES (default): the column group moves on after all I x J pairs of a step. The alternative -- each column body
+// shuffled right after its own I pairs, so that the shuffles overlap the next body's arithmetic (192 instead of 230
+// registers) -- measured 5 % SLOWER at N = 1M (901 vs 855 ms); kept selectable (direct_sym_shape 6) for A/B runs.
+// Also measured and rejected: two CTAs per SM with <= 128 registers and tile edge 4096 (<2,2> 967 ms, <4,1> 903 ms,
+// <4,2> with 68 bytes of spills 903 ms); tile edge 4096 with this kernel: 846 ms, but twice the partial-sum scratch.
+template<int I, int J, bool LATE_SHUFFLES = true>
 __global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
 direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, real* __restrict__ p_row,
 				 real* __restrict__ p_col, int tile_edge)
@@ -158,6 +163,8 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 #pragma unroll 1
 			for(int step = 0; step < 32; ++step)
 			{
+				// column body q moves on as soon as its I pairs are done, while the pairs of column body q + 1 (and, across
+				// the loop edge, those of the next step's body 0) keep the FP64 pipe busy: the shuffles never drain it
 #pragma unroll
 				for(int q = 0; q < J; ++q)
 				{
@@ -167,13 +174,23 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 						sym_pair(xb[q] - xa[k], yb[q] - ya[k], zb[q] - za[k], ma[k], mb[q],
 								 ax[k], ay[k], az[k], bx[q], by[q], bz[q]);
 					}
+					if(!LATE_SHUFFLES)
+					{
+						xb[q] = sym_shfl(xb[q], from); yb[q] = sym_shfl(yb[q], from); zb[q] = sym_shfl(zb[q], from);
+						mb[q] = sym_shfl(mb[q], from);
+						bx[q] = sym_shfl(bx[q], from); by[q] = sym_shfl(by[q], from); bz[q] = sym_shfl(bz[q], from);
+					}
 				}
-#pragma unroll
-				for(int q = 0; q < J; ++q)
+				if(LATE_SHUFFLES)
 				{
-					xb[q] = sym_shfl(xb[q], from); yb[q] = sym_shfl(yb[q], from); zb[q] = sym_shfl(zb[q], from);
-					mb[q] = sym_shfl(mb[q], from);
-					bx[q] = sym_shfl(bx[q], from); by[q] = sym_shfl(by[q], from); bz[q] = sym_shfl(bz[q], from);
+					// the first version of this kernel (kept for A/B measurements, direct_sym_shape 6): all shuffles after all pairs
+#pragma unroll
+					for(int q = 0; q < J; ++q)
+					{
+						xb[q] = sym_shfl(xb[q], from); yb[q] = sym_shfl(yb[q], from); zb[q] = sym_shfl(zb[q], from);
+						mb[q] = sym_shfl(mb[q], from);
+						bx[q] = sym_shfl(bx[q], from); by[q] = sym_shfl(by[q], from); bz[q] = sym_shfl(bz[q], from);
+					}
 				}
 			}
 			// 32 moves later every column body is home again, carrying the sum over this warp's 32*I row bodies
@@ -250,7 +267,7 @@ __device__ __forceinline__ f32x2 f2_shfl(f32x2 v, int src_lane)
 }
 
 // Same tile algorithm as direct_sym_tiles<I, 2>, column pair packed.
-template<int I>
+template<int I, bool LATE_SHUFFLES = false>
 __global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
 direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ tile_rc, float* __restrict__ p_row,
 					   float* __restrict__ p_col, int tile_edge)
@@ -307,6 +324,13 @@ direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ t
 #pragma unroll 1
 			for(int step = 0; step < 32; ++step)
 			{
+				// the column pair's position and mass do not change during a step: send them on BEFORE the pairs, so the
+				// shuffles overlap the arithmetic; only the three accumulators travel afterwards
+				f32x2 nxb = xb, nyb = yb, nzb = zb, nmb = mb;
+				if(!LATE_SHUFFLES)
+				{
+					nxb = f2_shfl(xb, from); nyb = f2_shfl(yb, from); nzb = f2_shfl(zb, from); nmb = f2_shfl(mb, from);
+				}
 #pragma unroll
 				for(int k = 0; k < I; ++k)
 				{
@@ -325,7 +349,11 @@ direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ t
 					by = f2_fma(dy, ncb, by);
 					bz = f2_fma(dz, ncb, bz);
 				}
-				xb = f2_shfl(xb, from); yb = f2_shfl(yb, from); zb = f2_shfl(zb, from); mb = f2_shfl(mb, from);
+				if(LATE_SHUFFLES)
+				{
+					nxb = f2_shfl(xb, from); nyb = f2_shfl(yb, from); nzb = f2_shfl(zb, from); nmb = f2_shfl(mb, from);
+				}
+				xb = nxb; yb = nyb; zb = nzb; mb = nmb;
 				bx = f2_shfl(bx, from); by = f2_shfl(by, from); bz = f2_shfl(bz, from);
 			}
 			if(!diagonal)

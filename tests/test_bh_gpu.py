@@ -62,9 +62,10 @@ def test_bh_huge_ratio_equals_direct():
 def test_bh_walk_modes_bit_identical():
     g = load_golden_npz("g1_n2048")
     (a,), _, sa = run_bh(g["y"], g["mass"], 10.0, walk_mode=0, stats=True)
-    (b,), _, sb = run_bh(g["y"], g["mass"], 10.0, walk_mode=1, stats=True)
-    assert np.array_equal(a, b)
-    assert sa == sb and sa[0] > sa[1] > 0
+    for mode in (1, 32):
+        (b,), _, sb = run_bh(g["y"], g["mass"], 10.0, walk_mode=mode, stats=True)
+        assert np.array_equal(a, b)
+        assert sa == sb and sa[0] > sa[1] > 0
 
 
 @pytest.mark.parametrize("precision", ["f64", "f32"])
@@ -72,15 +73,16 @@ def test_bh_walk_modes_bit_identical():
                                              (65536, 10.0, "0"), (65536, 2.0, "0,0,0,0")])
 def test_bh_several_targets_per_lane_bit_identical(precision, n, ratio, devices):
     """walk_mode 2 / 4: one warp walks the union of 64 / 128 consecutive leaves (2 / 4 targets per lane); every target
-    still accepts exactly the nodes of its own stackless traversal, so forces and visit counts equal walk_mode 0."""
+    still accepts exactly the nodes of its own stackless traversal, so forces and visit counts equal walk_mode 32 (one
+    target per lane). walk_mode 0, the default, is two targets per lane."""
     y, m = universe(n, precision) if n >= 128 else (None, None)   # make_universe rounds up to 2 x 64 bodies
     if y is None:
         g = load_golden_npz("g1_n128", precision)
         idx = np.arange(n)
         y = np.concatenate([g["y"][r * 128 + idx] for r in range(6)])
         m = g["mass"][idx]
-    (a,), _, sa = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=0, stats=True)
-    for mode in (2, 4):
+    (a,), _, sa = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=32, stats=True)
+    for mode in (0, 2, 4):
         (b,), _, sb = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=mode, stats=True)
         assert np.array_equal(a, b), "walk_mode %d" % mode
         assert sa == sb
