@@ -56,7 +56,7 @@ struct nbody_engine_b200::data
 	bool				m_step_graph;
 	void*				m_pinned[2];
 	data() : m_force(ef_direct), m_ratio(10), m_tree_build_rate(0), m_tree_layout(etl_heap_stackless),
-		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr), m_step_graph(false)
+		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr), m_step_graph(true)
 	{
 		m_pinned[0] = m_pinned[1] = nullptr;
 	}
@@ -624,7 +624,8 @@ nbody_engine* nbody_create_engine_b200(const QVariantMap& param)
 	}
 	engine->set_block_size(param.value("block_size", NBODY_DATA_BLOCK_SIZE).toInt());
 	engine->set_use_nccl(param.value("use_nccl", false).toBool());
-	engine->set_step_graph(param.value("step_graph", false).toBool());
+	// on by default: results are bit-identical to step_graph=0 (tests/test_stepgraph_gpu.py), ignored with several devices
+	engine->set_step_graph(param.value("step_graph", true).toBool());
 	return engine;
 }
 

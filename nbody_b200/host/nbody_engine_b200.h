@@ -66,7 +66,7 @@ public:
 	void set_block_size(int block_size);
 	//! Single-process lanes exchange shards by peer copies; NCCL is used by the one-process-per-GPU mode only
 	void set_use_nccl(bool);
-	//! Solver steps as CUDA graphs (factory parameter step_graph=1): a step that repeats the previous one call for call
+	//! Solver steps as CUDA graphs (factory parameter step_graph, default on): a step that repeats the previous one call for call
 	//! is replayed as one cudaGraphLaunch from advise_time(); results are those of the eager engine (include/nb200.h)
 	void set_step_graph(bool);
 	//! {graphs launched, replays abandoned, state, kernels per replayed step}

@@ -221,3 +221,40 @@ def test_fp32_adapter_euler_vs_reference_fp32(ref32):
     scale = np.abs(out["simple"]).max()
     assert np.abs(out["b200"] - out["simple"]).max() <= 2e-5 * scale
     assert np.abs(out["b200_bh"] - out["simple"]).max() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("kind,path", [("G1", "initial_state.txt"), ("SI", "initial_state.txt"), ("ADK", "initial_state.txt"),
+                                       ("Zeno", "zeno_ascii.txt")])
+def test_initial_state_types_direct_and_barnes_hut(ref64, adapter, kind, path):
+    """--initial_type G1 / SI / ADK / Zeno (nbody_data::load_initial, nbody_data.cpp:618-660: the unit system scales
+    the masses by G): the same loaded nbody_data on the reference's CPU engines and on the b200 aliases -- per-body
+    acceleration <= 1e-12 relative (direct vs openmp and block, Barnes-Hut vs simple_bh with the same tree layout and
+    opening ratio), and a short rk4 run ends in the same state."""
+    from oracle import refharness as R
+    bh = dict(distance_to_node_radius_ratio=10, tree_layout="heap_stackless")
+    pairs = [(dict(engine="openmp"), dict(engine="b200")),
+             (dict(engine="block"), dict(engine="b200")),
+             (dict(engine="simple_bh", traverse_type="nested_tree", **bh), dict(engine="b200_bh", **bh))]
+    for ref_kw, our_kw in pairs:
+        out = []
+        for make in (lambda: R.Engine(ref64, **ref_kw), lambda: b200_engine(ref64, adapter, **our_kw)):
+            d = R.Data(ref64).load_initial(golden_path(path), kind)
+            n = d.count
+            e = make()
+            assert e.init(d)
+            f = e.create_buffer(e.size(e.get_y()))
+            e.fcompute(0, e.get_y(), f)
+            acc = e.read_buffer(f).reshape(6, n)[3:]
+            e.free_buffer(f)
+            s = R.Solver(ref64, solver="rk4", max_step=1e-3, min_step=1e-9)
+            s.set_engine(e)
+            assert s.run(d, 5e-3) == 0
+            e.get_data(d)
+            out.append((acc, d.export()[0].copy()))
+            s.close()
+            e.close()
+            d.close()
+        (a_ref, y_ref), (a_our, y_our) = out
+        rel = np.sqrt(((a_ref - a_our) ** 2).sum(0)) / np.sqrt((a_ref ** 2).sum(0))
+        assert rel.max() <= 1e-12, "%s %r: %g" % (kind, our_kw, rel.max())
+        assert np.abs(y_ref - y_our).max() <= 1e-12 * max(1.0, np.abs(y_ref).max())
