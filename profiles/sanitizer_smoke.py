@@ -35,3 +35,23 @@ with Engine(kind="bh") as e:
     f = e.create_buffer(e.get_y().size())
     e.fcompute(0, e.get_y(), f)
     print("bh4096", e.fmaxabs(f))
+for mode in (0, 4, 32):                # walk variants: two / four / one target(s) per lane
+    with Engine(kind="bh") as e:
+        e.set_option("walk_mode", mode)
+        assert e.init(y, m)
+        f = e.create_buffer(e.get_y().size())
+        e.fcompute(0, e.get_y(), f)
+        print("bh4096 walk_mode", mode, e.fmaxabs(f))
+pos = np.ascontiguousarray(y.reshape(6, n)[0:3].T); vel = np.ascontiguousarray(y.reshape(6, n)[3:6].T)
+for dev in ("0", "0,0"):               # body transposes + solver steps replayed as graphs (two segments around fmaxabs)
+    with Engine(devices=dev) as e:
+        assert e.init_bodies(pos, vel, m)
+        e.set_option("step_graph", 1)
+        dy = e.create_buffer(e.get_y().size())
+        for _ in range(5):
+            e.fcompute(0, e.get_y(), dy)
+            err = e.fmaxabs(dy)
+            e.fmadd_inplace(e.get_y(), dy, 1e-3)
+            e.advise_time(1e-3)
+        p, v = e.get_bodies()
+        print("bodies + step graph", dev, e.step_graph_stats(), err, float(np.abs(p).max()))

@@ -228,12 +228,12 @@ def test_fp32_adapter_euler_vs_reference_fp32(ref32):
 def test_initial_state_types_direct_and_barnes_hut(ref64, adapter, kind, path):
     """--initial_type G1 / SI / ADK / Zeno (nbody_data::load_initial, nbody_data.cpp:618-660: the unit system scales
     the masses by G): the same loaded nbody_data on the reference's CPU engines and on the b200 aliases -- per-body
-    acceleration <= 1e-12 relative (direct vs openmp and block, Barnes-Hut vs simple_bh with the same tree layout and
+    acceleration <= 1e-12 relative (direct vs openmp, Barnes-Hut vs simple_bh with the same tree layout and
     opening ratio), and a short rk4 run ends in the same state."""
     from oracle import refharness as R
     bh = dict(distance_to_node_radius_ratio=10, tree_layout="heap_stackless")
+    # (the reference's block engine needs N % 64 == 0 -- these files hold 16 bodies -- so openmp is the direct oracle here)
     pairs = [(dict(engine="openmp"), dict(engine="b200")),
-             (dict(engine="block"), dict(engine="b200")),
              (dict(engine="simple_bh", traverse_type="nested_tree", **bh), dict(engine="b200_bh", **bh))]
     for ref_kw, our_kw in pairs:
         out = []
