@@ -44,10 +44,22 @@ def main():
         tmp = e.create_buffer(e.get_y().size())
         e.fmaddn(tmp, e.get_y(), [f], np.array([1e-3]))
         stage = e.read_buffer(tmp)
+        # body arrays <-> state vector across ranks: every rank uploads its own body range, every rank reads all bodies
+        pos, vel = e.get_bodies()
+        assert np.array_equal(pos.T.ravel(), y[:3 * n]) and np.array_equal(vel.T.ravel(), y[3 * n:])
+        ps, vs = e.get_bodies(y=tmp)
+        assert np.array_equal(np.concatenate([ps.T.ravel(), vs.T.ravel()]), stage)
+        assert e.set_option("step_graph", 1) == 0 and e.step_graph_stats()["state"] == "off"   # ignored with ranks
         mx = e.fmaxabs(tmp)                         # NCCL max all-reduce
         assert mx == np.abs(stage).max(), (mx, np.abs(stage).max())
         assert np.array_equal(stage, orc.fmaddn(stage, y, [got], np.array([1e-3])))
         e.close()
+        if label == "direct":
+            uid = dist.exchange_unique_id(lambda: new_unique_id("f64"))
+            with Engine(devices=[local], rank=rank, nranks=world, uid=uid) as eb:
+                yr = y.reshape(6, n)
+                assert eb.init_bodies(np.ascontiguousarray(yr[0:3].T), np.ascontiguousarray(yr[3:6].T), m)
+                assert np.array_equal(eb.read_buffer(eb.get_y()), y)
         results[kind] = got
         if rank == 0:
             with Engine(devices=[local], kind=kind, **kw) as single:
