@@ -1084,29 +1084,53 @@ int sym_tile_edge(const nb200_ctx* ctx)
 {
 	if(ctx->opt_direct_sym == 0) { return 0; }
 	if(ctx->lanes.size() > 1 && (ctx->nranks > 1 || !ctx->peer_loads || ctx->lanes.size() > NB200_SYM_MAX_PEERS)) { return 0; }
-	if(ctx->opt_direct_sym < 0 && ctx->n < 32768) { return 0; }	// too few tiles to fill 148 SMs
+	if(ctx->opt_direct_sym < 0 && ctx->n < NB200_SYM_MIN_BODIES) { return 0; }	// too few tiles to fill 148 SMs
 	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(3) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }	// partials > ~30 GB per rank
-	// automatic edge: ~N/128 (>= 8000 equal tiles), at most 8192 (192 KB of column sums; scratch 24 N^2 / T bytes)
+	// automatic edge: ~N/128 (>= 8000 equal tiles for N >= 32,768), at most 8192 (192 KB of column sums; scratch
+	// 24 N^2 / T bytes), at least 256 (the default kernels then run 2-warp / 1-warp CTAs, several per SM)
 	long long edge = ctx->opt_sym_tile;
 	if(edge <= 0)
 	{
-		edge = 1024;	// 8 row blocks of 128 bodies: the smallest tile that keeps all 8 warps busy
+		edge = 256;
 		while(edge * 2 <= static_cast<long long>(ctx->n / 128) && edge < 8192) { edge *= 2; }
 	}
-	// 8 column blocks per phase round, 32*J bodies each; 32*I bodies per row block
-	const long long unit = ctx->opt_sym_shape == 3 ? 1024 : (ctx->opt_sym_shape >= 1 ? 512 : 256);	// 6 = shape 1 with late shuffles
-	if(edge % unit != 0 || edge % 256 != 0 || edge > 8192) { return 0; }
+	// a power of two in [256, 8192]: the zero-mass padding of the packed sources (n_alloc) covers whole tiles of any such edge
+	if(edge > 8192 || edge < 256 || (edge & (edge - 1)) != 0) { return 0; }
+	if(ctx->opt_sym_shape == NB200_SYM_DEFAULT_SHAPE)
+	{
+		return static_cast<int>(edge);	// the CTA has as many warps as the tile has row blocks (1, 2, 4 or 8)
+	}
+	// the other shapes always run 8 warps: 8 column blocks per phase round, 32*J bodies each
+	const long long unit = ctx->opt_sym_shape == 3 ? 1024 : (ctx->opt_sym_shape >= 1 ? 512 : 256);
+	if(edge % unit != 0) { return 0; }
 	return static_cast<int>(edge);
 }
 
 template<class Kernel>
-int sym_launch(nb200_ctx* ctx, nb200_lane& l, Kernel kernel, size_t tiles, size_t smem, int T)
+int sym_launch(nb200_ctx* ctx, nb200_lane& l, Kernel kernel, size_t tiles, size_t smem, int T, int warps = NB200_SYM_WARPS)
 {
 	CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-	kernel<<<static_cast<unsigned>(tiles), NB200_SYM_THREADS, smem, l.stream>>>(
+	kernel<<<static_cast<unsigned>(tiles), 32 * warps, smem, l.stream>>>(
 		l.src, static_cast<const int2*>(l.sym_tiles), l.sym_prow, l.sym_pcol, T);
 	LAUNCHED(ctx);
 	return NB200_OK;
+}
+
+// The default kernel of this build, with as many warps per CTA as the tile has row blocks of 32 * I bodies
+int sym_launch_default(nb200_ctx* ctx, nb200_lane& l, size_t tiles, size_t smem, int T)
+{
+#if NB200_PRECISION == 1
+	const int row_blocks = T / 256;	// direct_sym_tiles_f32x2<8>
+	if(row_blocks >= 8) { return sym_launch(ctx, l, direct_sym_tiles_f32x2<8, false, 8>, tiles, smem, T, 8); }
+	if(row_blocks >= 4) { return sym_launch(ctx, l, direct_sym_tiles_f32x2<8, false, 4>, tiles, smem, T, 4); }
+	if(row_blocks >= 2) { return sym_launch(ctx, l, direct_sym_tiles_f32x2<8, false, 2>, tiles, smem, T, 2); }
+	return sym_launch(ctx, l, direct_sym_tiles_f32x2<8, false, 1>, tiles, smem, T, 1);
+#else
+	const int row_blocks = T / 128;	// direct_sym_tiles<4, 2>
+	if(row_blocks >= 8) { return sym_launch(ctx, l, direct_sym_tiles<4, 2, true, 8>, tiles, smem, T, 8); }
+	if(row_blocks >= 4) { return sym_launch(ctx, l, direct_sym_tiles<4, 2, true, 4>, tiles, smem, T, 4); }
+	return sym_launch(ctx, l, direct_sym_tiles<4, 2, true, 2>, tiles, smem, T, 2);
+#endif
 }
 
 // Tiles of shard `l.shard` (dealt round-robin over all shards) -> l.sym_acc = this shard's partial accelerations of
@@ -1158,15 +1182,17 @@ int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
 		int rc = NB200_OK;
 		switch(ctx->opt_sym_shape)
 		{
+		case NB200_SYM_DEFAULT_SHAPE: rc = sym_launch_default(ctx, l, mine, smem, T); break;
 #if NB200_PRECISION == 1
-		case 4: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<8>, mine, smem, T); break;	// packed f32x2
 		case 5: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<4>, mine, smem, T); break;
 		case 7: rc = sym_launch(ctx, l, direct_sym_tiles_f32x2<8, true>, mine, smem, T); break;	// all shuffles after the pairs (A/B)
 #endif
 		case 6: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2, false>, mine, smem, T); break;	// each column body shuffled right after its pairs (A/B: slower)
 		case 3: rc = sym_launch(ctx, l, direct_sym_tiles<4, 4>, mine, smem, T); break;
 		case 2: rc = sym_launch(ctx, l, direct_sym_tiles<8, 2>, mine, smem, T); break;
-		case 1: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2>, mine, smem, T); break;
+#if NB200_PRECISION == 1
+		case 1: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2>, mine, smem, T); break;	// scalar FP32 arithmetic
+#endif
 		default: rc = sym_launch(ctx, l, direct_sym_tiles<8, 1>, mine, smem, T); break;
 		}
 		if(rc != NB200_OK) { return rc; }

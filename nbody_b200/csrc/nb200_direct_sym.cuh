@@ -26,6 +26,20 @@
 
 #define NB200_SYM_WARPS 8
 #define NB200_SYM_THREADS (32 * NB200_SYM_WARPS)
+// direct_sym_shape of the kernel this build uses by default: FP64 1 = <4, 2> (4 row x 2 column bodies per lane),
+// FP32 4 = packed f32x2 with 8 row bodies; automatic from this many bodies on
+#if NB200_PRECISION == 1
+#define NB200_SYM_DEFAULT_SHAPE 4
+#else
+#define NB200_SYM_DEFAULT_SHAPE 1
+#endif
+// measured on one B200 (profiles/r1_direct_sizes.json): FP64 N = 8,192: 5.0e11 (ordered pairs) vs 6.0e11 pairs/s, FP32
+// N = 8,192: 9.4e11 vs 8.5e11, N = 16,384: 1.53e12 vs 1.57e12
+#if NB200_PRECISION == 1
+#define NB200_SYM_MIN_BODIES 16384
+#else
+#define NB200_SYM_MIN_BODIES 8192
+#endif
 
 #if NB200_PRECISION == 2
 __device__ __forceinline__ double sym_shfl(double v, int src_lane)
@@ -92,8 +106,10 @@ __device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_r
 // registers) -- measured 5 % SLOWER at N = 1M (901 vs 855 ms); kept selectable (direct_sym_shape 6) for A/B runs.
 // Also measured and rejected: two CTAs per SM with <= 128 registers and tile edge 4096 (<2,2> 967 ms, <4,1> 903 ms,
 // <4,2> with 68 bytes of spills 903 ms); tile edge 4096 with this kernel: 846 ms, but twice the partial-sum scratch.
-template<int I, int J, bool LATE_SHUFFLES = true>
-__global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
+// WARPS: warps per CTA. A tile needs T / (32 I) row blocks; with fewer than 8 of them (small tiles for small N) the
+// CTA shrinks instead of leaving warps idle, and several CTAs share an SM (230 registers x 128 threads fit twice).
+template<int I, int J, bool LATE_SHUFFLES = true, int WARPS = NB200_SYM_WARPS>
+__global__ void __launch_bounds__(32 * WARPS, NB200_SYM_MINB)
 direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, real* __restrict__ p_row,
 				 real* __restrict__ p_col, int tile_edge)
 {
@@ -111,13 +127,13 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 	const int	n_bblk = T / (32 * J);	// column blocks of the tile
 	const int	from = (lane + 31) & 31;	// the column group arrives from lane - 1
 
-	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	for(int e = threadIdx.x; e < 3 * T; e += 32 * WARPS)
 	{
 		colacc[e] = 0;
 	}
 	__syncthreads();
 
-	for(int a0 = 0; a0 < n_ablk; a0 += NB200_SYM_WARPS)
+	for(int a0 = 0; a0 < n_ablk; a0 += WARPS)
 	{
 		// every warp runs every phase (the phase barrier is block-wide); warps without a row block just keep step
 		const int	ablk = a0 + warp;
@@ -131,7 +147,7 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 			ax[k] = ay[k] = az[k] = 0;
 		}
 		// phase p: warp w owns column block (p + w * n_bblk / 8) mod n_bblk -- no two warps share a block in a phase
-		int		bblk = (warp * (n_bblk / NB200_SYM_WARPS)) % n_bblk;
+		int		bblk = (warp * (n_bblk / WARPS)) % n_bblk;
 		body4	nxt[J];
 #pragma unroll
 		for(int q = 0; q < J; ++q)
@@ -220,7 +236,7 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 			}
 		}
 	}
-	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	for(int e = threadIdx.x; e < 3 * T; e += 32 * WARPS)
 	{
 		out_col[e] = colacc[e];
 	}
@@ -267,8 +283,8 @@ __device__ __forceinline__ f32x2 f2_shfl(f32x2 v, int src_lane)
 }
 
 // Same tile algorithm as direct_sym_tiles<I, 2>, column pair packed.
-template<int I, bool LATE_SHUFFLES = false>
-__global__ void __launch_bounds__(NB200_SYM_THREADS, NB200_SYM_MINB)
+template<int I, bool LATE_SHUFFLES = false, int WARPS = NB200_SYM_WARPS>
+__global__ void __launch_bounds__(32 * WARPS, NB200_SYM_MINB)
 direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ tile_rc, float* __restrict__ p_row,
 					   float* __restrict__ p_col, int tile_edge)
 {
@@ -286,13 +302,13 @@ direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ t
 	const int	n_bblk = T / 64;
 	const int	from = (lane + 31) & 31;
 
-	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	for(int e = threadIdx.x; e < 3 * T; e += 32 * WARPS)
 	{
 		colacc[e] = 0;
 	}
 	__syncthreads();
 
-	for(int a0 = 0; a0 < n_ablk; a0 += NB200_SYM_WARPS)
+	for(int a0 = 0; a0 < n_ablk; a0 += WARPS)
 	{
 		const int	ablk = a0 + warp;
 		const bool	active = ablk < n_ablk;
@@ -305,7 +321,7 @@ direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ t
 			nma[k] = f2_pack(-b.m, -b.m);
 			ax[k] = ay[k] = az[k] = f2_pack(0.f, 0.f);
 		}
-		int		bblk = (warp * (n_bblk / NB200_SYM_WARPS)) % n_bblk;
+		int		bblk = (warp * (n_bblk / WARPS)) % n_bblk;
 		body4	nxt0 = cols[bblk * 64 + lane], nxt1 = cols[bblk * 64 + 32 + lane];
 		for(int p = 0; p < n_bblk; ++p)
 		{
@@ -380,7 +396,7 @@ direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ t
 			}
 		}
 	}
-	for(int e = threadIdx.x; e < 3 * T; e += NB200_SYM_THREADS)
+	for(int e = threadIdx.x; e < 3 * T; e += 32 * WARPS)
 	{
 		out_col[e] = colacc[e];
 	}

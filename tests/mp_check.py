@@ -29,7 +29,7 @@ def main():
     y, m = universe(n)
     orc = Oracle("f64")
     results = {}
-    for label, kind, kw, opts in (("direct", "direct", {}, ()),
+    for label, kind, kw, opts in (("direct", "direct", {}, (("direct_symmetric", 0),)),      # ordered pairs + all-gather
                                   ("direct-symmetric", "direct", {}, (("direct_symmetric", 1), ("direct_sym_tile", 2048))),
                                   ("bh", "bh", dict(distance_to_node_radius_ratio=3.1623), ())):
         uid = dist.exchange_unique_id(lambda: new_unique_id("f64"))

@@ -154,9 +154,9 @@ def test_multi_process_nccl_two_ranks():
     assert "mp_check direct ok" in out.stdout and "mp_check bh ok" in out.stdout and "mp_check direct-symmetric ok" in out.stdout
 
 
-# ---- symmetric (Newton's third law) tile path: automatic for N >= 32,768, forced here on small systems ------------
+# ---- symmetric (Newton's third law) tile path: automatic for N >= 8,192, forced here on small systems ------------
 @pytest.mark.parametrize("n,tile,shape", [(4096, 1024, 0), (8192, 2048, 0), (5000, 1024, 0), (4096, 1024, 1), (2048, 256, 0),
-                                          (3000, 512, 1)])
+                                          (3000, 512, 1), (2048, 256, 1), (1000, 256, 1), (4096, 512, 1)])
 def test_direct_symmetric_tiles_vs_oracle(oracle64, n, tile, shape):
     """Every unordered pair evaluated once and applied to both bodies; ragged N pads the last tile with zero-mass
     bodies; diagonal tiles are one-sided. Same 1e-12 gate as the plain kernel."""
@@ -232,7 +232,29 @@ def test_direct_symmetric_is_the_large_n_default(oracle64):
     assert np.all(np.abs(force) <= 1e-11 * scale)
 
 
-@pytest.mark.parametrize("n,tile,shape", [(4096, 1024, 2), (5000, 512, 1), (4096, 1024, 4), (5000, 512, 5), (3000, 1024, 4)])
+@pytest.mark.parametrize("precision,n,edge", [("f64", 8192, 256), ("f64", 16384, 256), ("f64", 65536, 512), ("f32", 16384, 256),
+                                              ("f32", 65536, 512)])
+def test_direct_symmetric_small_tiles_are_automatic(oracle64, precision, n, edge):
+    """From N = 8,192 (FP32: 16,384) the symmetric path is the default: tiles of 256 / 512 bodies run CTAs of 2 / 4 warps
+    (FP32: 1 / 2), several per SM. Sampled against the oracle, and Newton's third law over all bodies."""
+    y, m = universe(n, precision)
+    from nbody_b200 import Engine
+    with Engine(precision=precision) as e:
+        assert e.init(y, m)
+        fb = e.create_buffer(e.get_y().size())
+        e.fcompute(0.0, e.get_y(), fb)
+        assert e.last_direct_path() == edge
+        f = e.read_buffer(fb).astype(np.float64).reshape(6, n)
+    t = np.unique(np.concatenate([[0, n // 2, n - 1], np.random.RandomState(3).randint(0, n, 125)]))
+    ref = oracle64.accel_subset(y.astype(np.float64), m.astype(np.float64), t)
+    assert rel_err_per_body(f[3:, t], ref, t.size) <= (TOL64 if precision == "f64" else TOL32)
+    force = (f[3:] * m[None, :]).sum(axis=1)
+    scale = np.abs(f[3:] * m[None, :]).sum(axis=1)
+    assert np.all(np.abs(force) <= (1e-11 if precision == "f64" else 1e-3) * scale)
+
+
+@pytest.mark.parametrize("n,tile,shape", [(4096, 1024, 2), (5000, 512, 1), (4096, 1024, 4), (5000, 512, 5), (3000, 1024, 4),
+                                          (2048, 256, 4), (3000, 512, 4), (8192, 2048, 4)])
 def test_direct_symmetric_tiles_fp32(oracle32, oracle64, n, tile, shape):
     """Shapes 4 and 5 are the packed fma.rn.f32x2 kernels (two column bodies per instruction)."""
     rng = np.random.RandomState(n)
