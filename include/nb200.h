@@ -203,8 +203,9 @@ unsigned long long nb200_launch_count(const nb200_ctx* ctx);
  * out[0] = pack + gather, out[1] = tree build / refresh (BH only),
  * out[2] = force kernel (pairs or walk), out[3] = reduce/epilogue. Synchronises. */
 int nb200_last_fcompute_ms(nb200_ctx* ctx, float out[4]);
-/* Which kernel family the most recent nb200_fcompute_direct used: 0 = ordered-pair kernel (direct_pairs),
- * otherwise the tile edge of the symmetric-tile kernel (direct_sym_tiles). */
+/* Which kernel family the most recent nb200_fcompute_direct used: 0 = ordered-pair kernel (direct_pairs), -1 = the
+ * single-launch kernel for small systems (direct_small), otherwise the tile edge of the symmetric-tile kernel
+ * (direct_sym_tiles). */
 int nb200_last_direct_path(const nb200_ctx* ctx);
 /* CUDA-event stopwatch on lane 0's stream (the stream the kernels run on): nb200_mark records event
  * `slot` (0..7); nb200_elapsed_ms synchronises on slot b and returns the device time from a to b. */
@@ -213,7 +214,8 @@ int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms);
 /* FP64/FP32 FMA-pipe peak probe: runs a dependent-chain-free FMA kernel for
  * ~`ms` milliseconds and returns achieved FMA instructions (per lane) per second. */
 int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s);
-/* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "walk_mode" (0 = automatic: warp-coherent walk
+/* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "direct_symmetric" / "direct_small" (-1 automatic,
+ * 0 off, 1 on), "direct_sym_tile" (power of two, 256..8192), "walk_mode" (0 = automatic: warp-coherent walk
  * with two targets per lane; 1 = one thread per target; 2 / 4 = targets per lane; 32 = one target per lane), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
 int nb200_set_option(nb200_ctx* ctx, const char* name, long long value);
 

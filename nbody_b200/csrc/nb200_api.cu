@@ -1273,6 +1273,21 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	if(rc != NB200_OK) { return rc; }
 	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_direct: y and f must differ"); }
 	STEP_NOTE(ctx, make_op(SOP_FCOMPUTE_DIRECT, y, f));
+	if(ctx->nshards == 1 && ctx->opt_direct_small != 0 &&
+	   (ctx->opt_direct_small > 0 || (ctx->n <= NB200_SMALL_MAX_BODIES && ctx->opt_direct_sym < 0 && ctx->opt_direct_ipt == 0 && ctx->opt_direct_segments == 0)))
+	{
+		// small system: one launch does pairs, slice reduction and the velocity rows, straight from the state vector
+		nb200_lane& l = ctx->lanes[0];
+		CU(ctx, cudaSetDevice(l.dev));
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[0], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[1], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[2], l.stream)); }
+		const int n = static_cast<int>(ctx->n);
+		direct_small<<<static_cast<unsigned>((n + NB200_SMALL_TARGETS - 1) / NB200_SMALL_TARGETS), NB200_SMALL_TARGETS * NB200_SMALL_SLICES, 0, l.stream>>>(
+			lane_ptr(y, 0), l.mass, lane_ptr(f, 0), n);
+		LAUNCHED(ctx);
+		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[3], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }
+		ctx->last_direct_path = -1;
+		return NB200_OK;
+	}
 	rc = pack_and_gather(ctx, y);
 	if(rc != NB200_OK) { return rc; }
 	if(const int edge = sym_tile_edge(ctx))
@@ -1935,6 +1950,7 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = automatic, 1 = thread per target, 2 / 4 = targets per lane, 32 = one per lane
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
 	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; }	// -1 auto, 0 off, 1 on
+	else if(strcmp(name, "direct_small") == 0) { ctx->opt_direct_small = value; }	// -1 auto (N <= 4096), 0 off, 1 on
 	else if(strcmp(name, "direct_sym_tile") == 0) { ctx->opt_sym_tile = value; }
 	else if(strcmp(name, "direct_sym_shape") == 0) { ctx->opt_sym_shape = value; }
 	else if(strcmp(name, "timing") == 0) { ctx->opt_timing = value; }

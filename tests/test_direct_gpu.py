@@ -28,10 +28,16 @@ def run_direct(y, m, precision="f64", devices="0", options=()):
     return out
 
 
+# Up to N = 4,096 on one shard the automatic choice is the single-launch kernel (direct_small); direct_small=0 selects
+# the tiled ordered-pair kernel (pack + direct_pairs + direct_reduce) that larger and sharded systems use.
+SMALL_PATHS = pytest.mark.parametrize("path", [(), (("direct_small", 0),)], ids=["single-launch", "ordered-pairs"])
+
+
+@SMALL_PATHS
 @pytest.mark.parametrize("tag,n", [("g1_n128", 128), ("g1_n256", 256), ("g1_n2048", 2048)])
-def test_direct_vs_reference_engines_fp64(tag, n):
+def test_direct_vs_reference_engines_fp64(tag, n, path):
     g = load_golden_npz(tag)
-    f = run_direct(g["y"], g["mass"])
+    f = run_direct(g["y"], g["mass"], options=path)
     assert np.array_equal(f[:3 * n], g["y"][3 * n:])          # dr/dt = v, bit-exact
     assert rel_err_per_body(f, g["f_openmp"], n) <= TOL64
     assert rel_err_per_body(f, g["f_block"], n) <= TOL64
@@ -40,10 +46,11 @@ def test_direct_vs_reference_engines_fp64(tag, n):
     assert np.abs(f - g["f_simple"]).max() <= 1e-13 * max(1.0, np.abs(g["f_simple"]).max())
 
 
+@SMALL_PATHS
 @pytest.mark.parametrize("tag,n", [("g1_n128", 128), ("g1_n2048", 2048)])
-def test_direct_vs_reference_engines_fp32(oracle64, tag, n):
+def test_direct_vs_reference_engines_fp32(oracle64, tag, n, path):
     g = load_golden_npz(tag, "f32")
-    f = run_direct(g["y"], g["mass"], precision="f32")
+    f = run_direct(g["y"], g["mass"], precision="f32", options=path)
     assert np.array_equal(f[:3 * n], g["y"][3 * n:])
     assert rel_err_per_body(f, g["f_openmp"], n) <= TOL32
     # against FP64 arithmetic on the same FP32 inputs the GPU result is at least as accurate as the reference's
@@ -53,20 +60,23 @@ def test_direct_vs_reference_engines_fp32(oracle64, tag, n):
     assert err_gpu <= max(2 * err_ref, 2e-6), (err_gpu, err_ref)
 
 
-def test_direct_n16_golden_state(oracle64):
+@SMALL_PATHS
+def test_direct_n16_golden_state(oracle64, path):
     """N = 16 (the solver golden state): not a multiple of any tile size."""
     from oracle.oracle import load_table
     y, m = load_table(golden_path("initial_state.txt"))
-    f = run_direct(y, m)
+    f = run_direct(y, m, options=path)
     assert rel_err_per_body(f, oracle64.fcompute_openmp(y, m), 16) <= TOL64
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 129, 1000])
-def test_direct_ragged_sizes(oracle64, n):
+@SMALL_PATHS
+@pytest.mark.parametrize("n", [1, 2, 3, 15, 17, 129, 1000, 4096])
+def test_direct_ragged_sizes(oracle64, n, path):
     rng = np.random.RandomState(n)
     y = rng.uniform(-10, 10, 6 * n)
     m = rng.uniform(0.1, 2.0, n)
-    f = run_direct(y, m)
+    f = run_direct(y, m, options=path)
+    assert np.array_equal(f[:3 * n], y[3 * n:])
     ref = oracle64.fcompute_openmp(y, m)
     if n == 1:
         assert np.all(f[3:] == 0)
@@ -74,12 +84,13 @@ def test_direct_ragged_sizes(oracle64, n):
         assert rel_err_per_body(f, ref, n) <= TOL64
 
 
-def test_direct_coincident_bodies_use_min_distance(oracle64):
+@SMALL_PATHS
+def test_direct_coincident_bodies_use_min_distance(oracle64, path):
     """r^2 < 1e-8 is clamped to 1e-8 (nbody_data.cpp:39-42); coincident bodies contribute exactly 0."""
     y = np.zeros(6 * 4)
     y[0:4] = [0.0, 0.0, 5e-5, 1.0]          # bodies 0 and 1 coincide; body 2 is 5e-5 away (r^2 = 2.5e-9 < 1e-8)
     m = np.array([1.0, 2.0, 3.0, 4.0])
-    f = run_direct(y, m)
+    f = run_direct(y, m, options=path)
     ref = oracle64.fcompute_openmp(y, m)
     assert np.all(np.isfinite(f))
     assert np.allclose(f, ref, rtol=1e-13, atol=0)
@@ -94,11 +105,36 @@ def test_direct_all_kernel_shapes(ipt, segments):
     assert np.array_equal(f[:3 * 2048], g["y"][3 * 2048:])
 
 
-def test_direct_is_deterministic():
+@SMALL_PATHS
+def test_direct_is_deterministic(path):
     g = load_golden_npz("g1_n2048")
-    a = run_direct(g["y"], g["mass"])
-    b = run_direct(g["y"], g["mass"])
+    a = run_direct(g["y"], g["mass"], options=path)
+    b = run_direct(g["y"], g["mass"], options=path)
     assert np.array_equal(a, b)
+
+
+def test_direct_single_launch_kernel_is_the_small_n_default(oracle64):
+    """C1 (N = 2,048): fcompute is ONE kernel launch (pairs + slice reduction + velocity rows); above N = 4,096, with
+    several shards, or with a tiled-path tunable set, the tiled kernels run. Forced (direct_small=1) it handles any N."""
+    from nbody_b200 import Engine
+    g = load_golden_npz("g1_n2048")
+    for devices, opts, want_path, want_launches in (("0", (), -1, 1), ("0", (("direct_small", 0),), 0, 3), ("0,0", (), 0, 6),
+                                                    ("0", (("direct_segments", 4),), 0, 3)):
+        with Engine(devices=devices) as e:
+            for k, v in opts:
+                e.set_option(k, v)
+            assert e.init(g["y"], g["mass"])
+            f = e.create_buffer(e.get_y().size())
+            before = e.launch_count()
+            e.fcompute(0.0, e.get_y(), f)
+            assert e.last_direct_path() == want_path
+            assert e.launch_count() - before == want_launches
+            assert rel_err_per_body(e.read_buffer(f), g["f_openmp"], 2048) <= TOL64
+    n = 6000
+    rng = np.random.RandomState(6)
+    y, m = rng.uniform(-50, 50, 6 * n), rng.uniform(0.1, 2.0, n)
+    f = run_direct(y, m, options=(("direct_small", 1),))
+    assert rel_err_per_body(f, oracle64.fcompute_openmp(y, m), n) <= TOL64
 
 
 @pytest.mark.parametrize("devices", ["0,0", "0,0,0,0"])

@@ -95,7 +95,7 @@ def test_rk4_replayed_as_graphs_is_bit_identical(precision, kind, kw):
         assert st1["state"] == "replay"
         assert st1["graph_launches"] == steps - 1          # step 1 recorded eagerly, steps 2.. as graphs
         assert st1["bailouts"] == 0
-        assert st1["launches_per_step"] >= 9
+        assert st1["launches_per_step"] >= 8                  # direct at N = 2,048: 4 single-launch fcomputes + 4 state ops
         assert launches1 == launches0                        # the same kernels ran, only issued differently
 
 
