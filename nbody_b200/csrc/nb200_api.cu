@@ -1273,7 +1273,7 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 	if(rc != NB200_OK) { return rc; }
 	if(y == f) { return fail(ctx, NB200_ERR_ARG, "fcompute_direct: y and f must differ"); }
 	STEP_NOTE(ctx, make_op(SOP_FCOMPUTE_DIRECT, y, f));
-	if(ctx->nshards == 1 && ctx->opt_direct_small != 0 &&
+	if(ctx->nshards == 1 && ctx->opt_direct_small != 0 && ctx->n * sizeof(body4) <= NB200_SMALL_MAX_SMEM &&
 	   (ctx->opt_direct_small > 0 || (ctx->n <= NB200_SMALL_MAX_BODIES && ctx->opt_direct_sym < 0 && ctx->opt_direct_ipt == 0 && ctx->opt_direct_segments == 0)))
 	{
 		// small system: one launch does pairs, slice reduction and the velocity rows, straight from the state vector
@@ -1281,7 +1281,9 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 		CU(ctx, cudaSetDevice(l.dev));
 		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[0], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[1], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[2], l.stream)); }
 		const int n = static_cast<int>(ctx->n);
-		direct_small<<<static_cast<unsigned>((n + NB200_SMALL_TARGETS - 1) / NB200_SMALL_TARGETS), NB200_SMALL_TARGETS * NB200_SMALL_SLICES, 0, l.stream>>>(
+		const size_t smem = ctx->n * sizeof(body4);
+		CU(ctx, cudaFuncSetAttribute(direct_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		direct_small<<<static_cast<unsigned>((n + NB200_SMALL_TARGETS - 1) / NB200_SMALL_TARGETS), NB200_SMALL_TARGETS * NB200_SMALL_SLICES, smem, l.stream>>>(
 			lane_ptr(y, 0), l.mass, lane_ptr(f, 0), n);
 		LAUNCHED(ctx);
 		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[3], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[4], l.stream)); }

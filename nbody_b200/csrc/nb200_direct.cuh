@@ -346,39 +346,46 @@ __global__ void __launch_bounds__(256) direct_reduce(const real* __restrict__ pa
 // ---- small systems: ONE launch per fcompute -----------------------------------------------------------------------
 // Up to a few thousand bodies the three launches of the tiled path (pack, pairs, reduce) cost more than the pairs
 // themselves (C1, N = 2,048: 4.2e6 pairs are ~5 us of FP64 work). Here a CTA of 256 threads owns 16 targets x 16 source
-// slices and reads the state vector and the masses directly: thread (target t, slice s) sums sources s, s + 16, ...
+// slices, stages the whole system from the state vector and the masses into shared memory (N * 32 bytes), and thread
+// (target t, slice s) sums sources s, s + 16, ...
 // (two interleaved accumulator sets for ILP), the 16 slice sums of a target are then added in shared memory in slice
 // order -- a fixed order, so results are bit-reproducible -- and the same kernel copies the velocity rows. Same pair
 // arithmetic and exact MinDistance clamp as everywhere else. Single-shard contexts only.
 #define NB200_SMALL_TARGETS 16
 #define NB200_SMALL_SLICES 16
 #define NB200_SMALL_MAX_BODIES 4096
+#define NB200_SMALL_MAX_SMEM (200 * 1024)	// forced (direct_small = 1): up to 6400 FP64 / 12800 FP32 bodies
 __global__ void __launch_bounds__(NB200_SMALL_TARGETS * NB200_SMALL_SLICES)
 direct_small(const real* __restrict__ y, const real* __restrict__ mass, real* __restrict__ f, int n)
 {
+	extern __shared__ __align__(32) unsigned char small_smem[];
+	body4*		src = reinterpret_cast<body4*>(small_smem);	// all n bodies, packed (n * sizeof(body4) bytes, <= 128 KB)
 	__shared__ real part[3][NB200_SMALL_SLICES][NB200_SMALL_TARGETS];
+	// every CTA stages the whole system once: coalesced, independent loads -> one memory round trip instead of one
+	// per source (the state vector of a small system sits in L2)
+	for(int j = threadIdx.x; j < n; j += NB200_SMALL_TARGETS * NB200_SMALL_SLICES)
+	{
+		body4 b;
+		b.x = y[j]; b.y = y[n + j]; b.z = y[2 * n + j]; b.m = mass[j];
+		src[j] = b;
+	}
+	__syncthreads();
 	const int	t = threadIdx.x % NB200_SMALL_TARGETS;
 	const int	sl = threadIdx.x / NB200_SMALL_TARGETS;
 	const int	i = blockIdx.x * NB200_SMALL_TARGETS + t;
-	const int	ic = i < n ? i : n - 1;	// idle targets shadow the last body and never store
-	const real	xi = y[ic], yi = y[n + ic], zi = y[2 * n + ic];
+	const body4	me = src[i < n ? i : n - 1];	// idle targets shadow the last body and never store
 	real		ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
 	int			j = sl;
 	for(; j + NB200_SMALL_SLICES < n; j += 2 * NB200_SMALL_SLICES)
 	{
-		// half a warp shares a slice: every load is a two-address broadcast
-		body4 s0, s1;
-		s0.x = y[j]; s0.y = y[n + j]; s0.z = y[2 * n + j]; s0.m = mass[j];
-		const int j1 = j + NB200_SMALL_SLICES;
-		s1.x = y[j1]; s1.y = y[n + j1]; s1.z = y[2 * n + j1]; s1.m = mass[j1];
-		pair_interaction(xi, yi, zi, s0, ax0, ay0, az0);
-		pair_interaction(xi, yi, zi, s1, ax1, ay1, az1);
+		// half a warp shares a slice: every shared-memory read is a two-address broadcast
+		const body4 s0 = src[j], s1 = src[j + NB200_SMALL_SLICES];
+		pair_interaction(me.x, me.y, me.z, s0, ax0, ay0, az0);
+		pair_interaction(me.x, me.y, me.z, s1, ax1, ay1, az1);
 	}
 	if(j < n)
 	{
-		body4 s0;
-		s0.x = y[j]; s0.y = y[n + j]; s0.z = y[2 * n + j]; s0.m = mass[j];
-		pair_interaction(xi, yi, zi, s0, ax0, ay0, az0);
+		pair_interaction(me.x, me.y, me.z, src[j], ax0, ay0, az0);
 	}
 	part[0][sl][t] = ax0 + ax1;
 	part[1][sl][t] = ay0 + ay1;
