@@ -290,6 +290,7 @@ int step_bail(nb200_ctx* ctx)
 	step_graph& sg = *ctx->sg;
 	const size_t first = sg.seg_start, upto = sg.pos;
 	++sg.bailouts;
+	sg.replayed_in_a_row = 0;
 	sg.mode = SG_RECORD;
 	step_drop_graphs(ctx);
 	int rc = step_issue_range(ctx, sg.seq, first, upto);
@@ -1282,7 +1283,12 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 		if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[0], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[1], l.stream)); CU(ctx, cudaEventRecord(l.ev_t[2], l.stream)); }
 		const int n = static_cast<int>(ctx->n);
 		const size_t smem = ctx->n * sizeof(body4);
-		CU(ctx, cudaFuncSetAttribute(direct_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+		if(l.small_smem == 0)
+		{
+			// the same ceiling from every context of the process, so that none lowers what another one relies on
+			CU(ctx, cudaFuncSetAttribute(direct_small, cudaFuncAttributeMaxDynamicSharedMemorySize, NB200_SMALL_MAX_SMEM));
+			l.small_smem = NB200_SMALL_MAX_SMEM;
+		}
 		direct_small<<<static_cast<unsigned>((n + NB200_SMALL_TARGETS - 1) / NB200_SMALL_TARGETS), NB200_SMALL_TARGETS * NB200_SMALL_SLICES, smem, l.stream>>>(
 			lane_ptr(y, 0), l.mass, lane_ptr(f, 0), n);
 		LAUNCHED(ctx);
@@ -1789,6 +1795,9 @@ NB200_API int nb200_step_boundary(nb200_ctx* ctx)
 				++sg.graph_launches;
 			}
 			sg.pos = sg.seg = sg.seg_start = 0;
+			// a long run of replayed steps pays for the occasional abandoned one (an adaptive solver that subdivides now
+			// and then): forget old failures, so that only callers whose steps never repeat end up eager for good
+			if(++sg.replayed_in_a_row >= 16) { sg.failures = 0; }
 			return NB200_OK;
 		}
 		rc = step_bail(ctx);	// the step ended before the recorded one did

@@ -53,6 +53,7 @@ struct nb200_lane
 	body4*			src = nullptr;      // packed sources for all N bodies (+ zero-mass padding)
 	real*			partial = nullptr;  // [S][3][n_shard] partial accelerations (direct, S>1)
 	size_t			partial_elems = 0;
+	size_t			small_smem = 0;     // dynamic shared memory direct_small has been allowed so far
 	// symmetric-tile path (nb200_direct_sym.cuh)
 	void*			sym_tiles = nullptr;	// int2 {row block, column block} of this rank's tiles
 	real*			sym_prow = nullptr;		// [tiles][3][T] row sums

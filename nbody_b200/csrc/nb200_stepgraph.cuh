@@ -79,6 +79,7 @@ struct step_graph
 	bool					busy = false;	// re-entrancy guard while deferred calls are issued
 	long long				saved_timing = 0;
 	int						failures = 0;	// captures that did not lead to a replay; gives up after a few
+	int						replayed_in_a_row = 0;	// steps replayed since the last abandoned one (16 of them clear `failures`)
 	// one graph per segment of the recorded step (segments are separated by fmaxabs calls; nullptr = empty segment)
 	std::vector<cudaGraphExec_t>	execs;
 	std::vector<unsigned long long>	seg_launches;	// kernel launches inside each segment
