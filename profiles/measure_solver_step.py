@@ -47,9 +47,19 @@ def main():
         ad.nbody_engine_b200_synchronize(h)
         dt = (time.perf_counter() - t0) / steps
         cc, launches = (e.compute_count() - cc0) // steps, (ad.nbody_engine_b200_launch_count(h) - l0) // steps
-        # every fcompute is 3 launches (pack, pairs, reduce); the rest are state-vector kernels
+        # split of the step: the same number of fcompute calls alone, on the same state, timed the same way
+        fbuf = e.create_buffer(e.size(e.get_y()))
+        e.fcompute(0, e.get_y(), fbuf)
+        ad.nbody_engine_b200_synchronize(h)
+        t1 = time.perf_counter()
+        for _ in range(cc):
+            e.fcompute(0, e.get_y(), fbuf)
+        ad.nbody_engine_b200_synchronize(h)
+        t_fc = time.perf_counter() - t1
+        e.free_buffer(fbuf)
         out["rows"].append({"solver": name, "s_per_step": dt, "fcompute_per_step": cc, "launches_per_step": launches,
-                            "state_op_launches_per_step": launches - 3 * cc, "pairs_per_s": cc * float(n) * n / dt})
+                            "fcompute_s_per_step": t_fc, "state_ops_s_per_step": max(dt - t_fc, 0.0),
+                            "state_ops_share": max(dt - t_fc, 0.0) / dt, "pairs_per_s": cc * float(n) * n / dt})
         s.close()
         e.close()
         d.close()
