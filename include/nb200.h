@@ -185,16 +185,17 @@ int nb200_host_register(nb200_ctx* ctx, void* host, size_t bytes);
 int nb200_host_unregister(nb200_ctx* ctx, void* host);
 
 /* ---- solver steps as CUDA graphs ---------------------------------------------------------------
- * With nb200_set_option(ctx, "step_graph", 1) the library watches the calls between two step boundaries. A step
- * that repeats the previous one call for call (same operations, buffers and scalars, nothing host-visible inside:
- * every fixed-step solver of the reference, e.g. nbody_solver_rk4.cpp:30-62) is captured once into a CUDA graph and
- * from then on launched as ONE graph per step; any deviation falls back to issuing the calls one by one, so results
- * never differ from the eager engine. The adapter calls nb200_step_boundary from advise_time(), which every solver
+ * With nb200_set_option(ctx, "step_graph", 1) the library watches the calls between two step boundaries and files
+ * every distinct step (same operations, buffers and scalars, nothing host-visible inside except fmaxabs) in a small
+ * table, together with the step that followed it. A step predicted to repeat a filed one is captured once into a
+ * CUDA graph and from then on launched as ONE graph per step (e.g. nbody_solver_rk4.cpp:30-62; periodic patterns --
+ * Adams' rotating history, Bulirsch-Stoer's sub-steps, tree_build_rate -- take one entry per phase); any deviation
+ * falls back to issuing the calls one by one, so results never differ from the eager engine. The adapter calls nb200_step_boundary from advise_time(), which every solver
  * calls exactly once at the end of a step. Single-shard contexts only (ignored with lanes or ranks). */
 int nb200_step_boundary(nb200_ctx* ctx);
-/* out[0] = graphs launched, out[1] = replays abandoned, out[2] = state (0 off, 1 record, 2 capture, 3 replay),
- * out[3] = kernel launches inside one replayed step. */
-int nb200_step_graph_stats(const nb200_ctx* ctx, unsigned long long out[4]);
+/* out[0] = graphs launched, out[1] = replays abandoned, out[2] = state of the NEXT step (0 off, 1 record, 2 capture,
+ * 3 replay), out[3] = kernel launches inside the step replayed last, out[4] = distinct steps in the table. */
+int nb200_step_graph_stats(const nb200_ctx* ctx, unsigned long long out[5]);
 
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of nb200 kernels launched since creation (all lanes). */

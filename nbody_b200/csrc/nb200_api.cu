@@ -241,11 +241,10 @@ int step_issue(nb200_ctx* ctx, const step_op& op)
 	}
 }
 
-void step_drop_graphs(nb200_ctx* ctx)
+void step_destroy_execs(nb200_ctx* ctx, std::vector<cudaGraphExec_t>& execs)
 {
-	step_graph& sg = *ctx->sg;
 	bool synced = false;
-	for(cudaGraphExec_t e : sg.execs)
+	for(cudaGraphExec_t e : execs)
 	{
 		if(e == nullptr) { continue; }
 		if(!synced)
@@ -256,19 +255,30 @@ void step_drop_graphs(nb200_ctx* ctx)
 		}
 		cudaGraphExecDestroy(e);
 	}
-	sg.execs.clear();
-	sg.seg_launches.clear();
+	execs.clear();
 }
 
-void step_failure(nb200_ctx* ctx)
+// Forget every step seen so far (and free the graphs)
+void step_clear_table(nb200_ctx* ctx)
 {
 	step_graph& sg = *ctx->sg;
-	if(++sg.failures > NB200_STEP_GRAPH_MAX_FAILURES)
+	for(step_entry& e : sg.entries) { step_destroy_execs(ctx, e.execs); }
+	sg.entries.clear();
+	sg.last = sg.target = -1;
+}
+
+// Mispredicted step. Callers whose steps never repeat are never predicted for and never get here; this only stops a
+// caller whose steps repeat just often enough to be predicted and then always differ.
+void step_miss(nb200_ctx* ctx)
+{
+	step_graph& sg = *ctx->sg;
+	if(++sg.misses > NB200_STEP_GRAPH_MAX_MISSES)
 	{
-		step_drop_graphs(ctx);
-		sg.seq.clear();
+		step_clear_table(ctx);
+		step_destroy_execs(ctx, sg.cap_execs);
+		sg.cap_launches.clear();
 		sg.cur.clear();
-		sg.mode = SG_OFF;	// this caller's steps do not repeat: stay eager
+		sg.mode = SG_OFF;
 	}
 }
 
@@ -284,20 +294,19 @@ int step_issue_range(nb200_ctx* ctx, const std::vector<step_op>& ops, size_t fir
 }
 
 // Replay ends early: the calls accepted since the last segment border have not run yet. Run them, then carry on as a
-// recording (earlier segments of this step already ran as graphs).
+// recording (earlier segments of this step already ran as graphs). The entry keeps its graphs for later steps.
 int step_bail(nb200_ctx* ctx)
 {
 	step_graph& sg = *ctx->sg;
+	const std::vector<step_op>& seq = sg.entries[static_cast<size_t>(sg.target)].seq;
 	const size_t first = sg.seg_start, upto = sg.pos;
 	++sg.bailouts;
-	sg.replayed_in_a_row = 0;
 	sg.mode = SG_RECORD;
-	step_drop_graphs(ctx);
-	int rc = step_issue_range(ctx, sg.seq, first, upto);
-	sg.cur.assign(sg.seq.begin(), sg.seq.begin() + static_cast<std::ptrdiff_t>(upto));
-	sg.seq.clear();
+	int rc = step_issue_range(ctx, seq, first, upto);
+	sg.cur.assign(seq.begin(), seq.begin() + static_cast<std::ptrdiff_t>(upto));
 	sg.pos = sg.seg = sg.seg_start = 0;
-	step_failure(ctx);
+	sg.target = -1;
+	step_miss(ctx);
 	return rc;
 }
 
@@ -315,14 +324,14 @@ int step_begin_segment(nb200_ctx* ctx)
 	return NB200_OK;
 }
 
-// Close the segment being captured (if any), run it, and keep its graph as segment number execs.size().
+// Close the segment being captured (if any), run it, and keep its graph as segment number cap_execs.size().
 int step_close_segment(nb200_ctx* ctx)
 {
 	step_graph&	sg = *ctx->sg;
 	if(!sg.capturing)
 	{
-		sg.execs.push_back(nullptr);	// an empty segment (two borders in a row, or a border first)
-		sg.seg_launches.push_back(0);
+		sg.cap_execs.push_back(nullptr);	// an empty segment (two borders in a row, or a border first)
+		sg.cap_launches.push_back(0);
 		return NB200_OK;
 	}
 	nb200_lane&	l = ctx->lanes[0];
@@ -341,18 +350,19 @@ int step_close_segment(nb200_ctx* ctx)
 		cudaGetLastError();
 		if(exec != nullptr) { cudaGraphExecDestroy(exec); }
 		sg.mode = SG_OFF;
-		step_drop_graphs(ctx);
+		step_clear_table(ctx);
+		step_destroy_execs(ctx, sg.cap_execs);
+		sg.cap_launches.clear();
 		std::vector<step_op> lost;
 		lost.swap(sg.cur);
-		sg.seq.clear();
 		ctx->launches = sg.launches_at_begin;
 		int rc = step_issue_range(ctx, lost, sg.cur_seg_start, lost.size());
 		if(rc != NB200_OK) { return rc; }
 		ctx->err = std::string("step graph: capture failed (") + cudaGetErrorString(res) + "), continuing eagerly";
 		return NB200_OK;
 	}
-	sg.execs.push_back(exec);
-	sg.seg_launches.push_back(ctx->launches - sg.launches_at_begin);
+	sg.cap_execs.push_back(exec);
+	sg.cap_launches.push_back(ctx->launches - sg.launches_at_begin);
 	++sg.graph_launches;
 	return NB200_OK;
 }
@@ -373,24 +383,25 @@ int step_break(nb200_ctx* ctx)
 		rc = step_close_segment(ctx);
 		if(sg.mode != SG_OFF)
 		{
-			step_drop_graphs(ctx);
+			step_destroy_execs(ctx, sg.cap_execs);	// a step with a host-visible call inside is not kept
+			sg.cap_launches.clear();
 			sg.mode = SG_RECORD;
-			step_failure(ctx);
+			sg.target = -1;
+			step_miss(ctx);
 		}
 	}
 	if(!sg.cur.empty()) { sg.clean = false; }
 	return rc;
 }
 
-// Buffers or configuration changed: a recorded step no longer describes what the caller will do.
+// Buffers or configuration changed: the recorded steps no longer describe what the caller will do.
 int step_invalidate(nb200_ctx* ctx)
 {
 	step_graph& sg = *ctx->sg;
 	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
 	int rc = step_break(ctx);
 	if(sg.mode == SG_OFF) { return rc; }
-	step_drop_graphs(ctx);
-	sg.seq.clear();
+	step_clear_table(ctx);
 	sg.pos = sg.seg = sg.seg_start = 0;
 	sg.mode = SG_RECORD;
 	return rc;
@@ -401,11 +412,50 @@ int step_overflow(nb200_ctx* ctx)
 	// nobody marks step boundaries: stop watching
 	step_graph& sg = *ctx->sg;
 	int rc = sg.capturing ? step_close_segment(ctx) : NB200_OK;
-	step_drop_graphs(ctx);
+	step_destroy_execs(ctx, sg.cap_execs);
+	sg.cap_launches.clear();
+	step_clear_table(ctx);
 	sg.cur.clear();
-	sg.seq.clear();
 	sg.mode = SG_OFF;
 	return rc;
+}
+
+// The call at hand is not what the predicted entry has at this position. Another entry may agree with everything
+// accepted so far AND with this call: then the prediction was wrong, not the idea of replaying.
+//   * such an entry with graphs: carry on replaying against it (segments launched so far came from the old entry's
+//     graphs, which hold the same calls) -- returns 1, the call is accepted;
+//   * such an entry without graphs, and no segment border passed yet: capture it now -- the capture starts with the
+//     calls accepted so far, issued into it -- returns 2, the caller issues the call (into the capture);
+//   * otherwise returns 0: the replay is abandoned (step_bail).
+int step_retarget(nb200_ctx* ctx, const step_op& op)
+{
+	step_graph& sg = *ctx->sg;
+	const std::vector<step_op>& have = sg.entries[static_cast<size_t>(sg.target)].seq;
+	int uncaptured = -1;
+	for(size_t k = 0; k < sg.entries.size(); ++k)
+	{
+		const step_entry& e = sg.entries[k];
+		if(static_cast<int>(k) == sg.target || e.seq.size() <= sg.pos || !e.seq[sg.pos].same(op)) { continue; }
+		bool prefix = true;
+		for(size_t q = 0; prefix && q < sg.pos; ++q) { prefix = e.seq[q].same(have[q]); }
+		if(!prefix) { continue; }
+		if(e.captured)
+		{
+			sg.target = static_cast<int>(k);
+			return 1;
+		}
+		if(uncaptured < 0) { uncaptured = static_cast<int>(k); }
+	}
+	if(uncaptured < 0 || sg.seg != 0 || op.kind == SOP_FMAXABS) { return 0; }
+	const size_t upto = sg.pos;
+	sg.cur.clear();
+	if(step_begin_segment(ctx) != NB200_OK) { return 0; }
+	sg.mode = SG_CAPTURE;
+	if(step_issue_range(ctx, have, 0, upto) != NB200_OK) { return 0; }
+	sg.cur.assign(have.begin(), have.begin() + static_cast<std::ptrdiff_t>(upto));
+	sg.target = uncaptured;
+	sg.pos = sg.seg = sg.seg_start = 0;
+	return 2;
 }
 
 // Every deferrable call reports itself here after validating its arguments. *skip: the call is part of the replayed
@@ -417,14 +467,25 @@ int step_note(nb200_ctx* ctx, const step_op& op, bool* skip)
 	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
 	if(sg.mode == SG_REPLAY)
 	{
-		if(sg.pos < sg.seq.size() && sg.seq[sg.pos].same(op))
+		const std::vector<step_op>& seq = sg.entries[static_cast<size_t>(sg.target)].seq;
+		if(sg.pos < seq.size() && seq[sg.pos].same(op))
 		{
 			++sg.pos;
 			*skip = true;
 			return NB200_OK;
 		}
-		int rc = step_bail(ctx);
-		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+		const int other = step_retarget(ctx, op);
+		if(other == 1)
+		{
+			++sg.pos;
+			*skip = true;
+			return NB200_OK;
+		}
+		if(other == 0)
+		{
+			int rc = step_bail(ctx);
+			if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+		}
 	}
 	if(sg.mode == SG_CAPTURE && !sg.capturing)
 	{
@@ -444,14 +505,15 @@ int step_border(nb200_ctx* ctx, const step_op& op)
 	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
 	if(sg.mode == SG_REPLAY)
 	{
-		if(sg.pos < sg.seq.size() && sg.seq[sg.pos].same(op))
+		const step_entry& e = sg.entries[static_cast<size_t>(sg.target)];
+		if(sg.pos < e.seq.size() && e.seq[sg.pos].same(op))
 		{
 			nb200_lane& l = ctx->lanes[0];
-			if(sg.execs[sg.seg] != nullptr)
+			if(e.execs[sg.seg] != nullptr)
 			{
 				CU(ctx, cudaSetDevice(l.dev));
-				CU(ctx, cudaGraphLaunch(sg.execs[sg.seg], l.stream));
-				ctx->launches += sg.seg_launches[sg.seg];
+				CU(ctx, cudaGraphLaunch(e.execs[sg.seg], l.stream));
+				ctx->launches += e.seg_launches[sg.seg];
 				++sg.graph_launches;
 			}
 			++sg.seg;
@@ -460,6 +522,23 @@ int step_border(nb200_ctx* ctx, const step_op& op)
 			return NB200_OK;
 		}
 		if(sg.pos == 0) { return NB200_OK; }	// a stray reduction between steps
+		if(step_retarget(ctx, op) == 1)
+		{
+			// another entry has the border here too: the segment before it holds the same calls in both
+			const step_entry& t = sg.entries[static_cast<size_t>(sg.target)];
+			if(t.execs[sg.seg] != nullptr)
+			{
+				nb200_lane& l = ctx->lanes[0];
+				CU(ctx, cudaSetDevice(l.dev));
+				CU(ctx, cudaGraphLaunch(t.execs[sg.seg], l.stream));
+				ctx->launches += t.seg_launches[sg.seg];
+				++sg.graph_launches;
+			}
+			++sg.seg;
+			++sg.pos;
+			sg.seg_start = sg.pos;
+			return NB200_OK;
+		}
 		int rc = step_bail(ctx);
 		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
 	}
@@ -470,6 +549,21 @@ int step_border(nb200_ctx* ctx, const step_op& op)
 	}
 	sg.cur.push_back(op);
 	return sg.cur.size() > 65536 ? step_overflow(ctx) : NB200_OK;
+}
+
+// The table entry with exactly these calls (filed if new); -1 for an empty step
+int step_find_or_add(nb200_ctx* ctx, std::vector<step_op>& calls)
+{
+	step_graph& sg = *ctx->sg;
+	if(calls.empty()) { return -1; }
+	for(size_t k = 0; k < sg.entries.size(); ++k)
+	{
+		if(step_same_sequence(sg.entries[k].seq, calls)) { return static_cast<int>(k); }
+	}
+	if(sg.entries.size() >= NB200_STEP_GRAPH_MAX_ENTRIES) { step_clear_table(ctx); }	// too many distinct steps: start over
+	sg.entries.emplace_back();
+	sg.entries.back().seq.swap(calls);
+	return static_cast<int>(sg.entries.size()) - 1;
 }
 
 #define STEP_NOTE(ctx, op)                                                                             \
@@ -654,7 +748,8 @@ NB200_API int nb200_destroy(nb200_ctx* ctx)
 	if(ctx->sg != nullptr && !ctx->lanes.empty() && ctx->lanes[0].stream != nullptr)
 	{
 		step_invalidate(ctx);	// issues whatever a replayed step still holds back
-		step_drop_graphs(ctx);
+		step_clear_table(ctx);
+		step_destroy_execs(ctx, ctx->sg->cap_execs);
 		ctx->sg->mode = SG_OFF;
 	}
 	for(auto& l : ctx->lanes)
@@ -1410,7 +1505,10 @@ NB200_API int nb200_fcompute_bh(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f
 	}
 	{
 		step_op op = make_op(SOP_FCOMPUTE_BH, y, f);
-		op.step = ctx->bh_build_rate == 0 ? 0 : step;	// the step number only matters when the tree is kept for several steps
+		op.step = step;
+		// the step number only matters through "does this call rebuild the tree" (a first call always does: the table is
+		// emptied by set_bodies, and the first step after that runs eagerly)
+		op.key = ctx->bh_build_rate == 0 ? 0 : (step % ctx->bh_build_rate == 0 ? 1 : 2);
 		STEP_NOTE(ctx, op);
 	}
 	rc = pack_and_gather(ctx, y);
@@ -1781,74 +1879,97 @@ NB200_API int nb200_step_boundary(nb200_ctx* ctx)
 	step_graph& sg = *ctx->sg;
 	if(sg.mode == SG_OFF || sg.busy) { return NB200_OK; }
 	int rc = NB200_OK;
+	int me = -1;	// the table entry of the step that ends here
 	if(sg.mode == SG_REPLAY)
 	{
 		if(sg.pos == 0) { return NB200_OK; }	// no calls since the last boundary
-		if(sg.pos == sg.seq.size())
+		if(sg.pos != sg.entries[static_cast<size_t>(sg.target)].seq.size())
 		{
-			if(sg.execs[sg.seg] != nullptr)
+			// the step ended before the predicted one did; it may be exactly another entry that has graphs
+			const std::vector<step_op>& have = sg.entries[static_cast<size_t>(sg.target)].seq;
+			for(size_t k = 0; k < sg.entries.size(); ++k)
+			{
+				const step_entry& alt = sg.entries[k];
+				if(!alt.captured || alt.seq.size() != sg.pos) { continue; }
+				bool prefix = true;
+				for(size_t q = 0; prefix && q < sg.pos; ++q) { prefix = alt.seq[q].same(have[q]); }
+				if(prefix)
+				{
+					sg.target = static_cast<int>(k);
+					break;
+				}
+			}
+		}
+		const step_entry& e = sg.entries[static_cast<size_t>(sg.target)];
+		if(sg.pos == e.seq.size())
+		{
+			if(e.execs[sg.seg] != nullptr)
 			{
 				nb200_lane& l = ctx->lanes[0];
 				CU(ctx, cudaSetDevice(l.dev));
-				CU(ctx, cudaGraphLaunch(sg.execs[sg.seg], l.stream));
-				ctx->launches += sg.seg_launches[sg.seg];
+				CU(ctx, cudaGraphLaunch(e.execs[sg.seg], l.stream));
+				ctx->launches += e.seg_launches[sg.seg];
 				++sg.graph_launches;
 			}
-			sg.pos = sg.seg = sg.seg_start = 0;
-			// a long run of replayed steps pays for the occasional abandoned one (an adaptive solver that subdivides now
-			// and then): forget old failures, so that only callers whose steps never repeat end up eager for good
-			if(++sg.replayed_in_a_row >= 16) { sg.failures = 0; }
-			return NB200_OK;
+			sg.launches_per_step = 0;
+			for(unsigned long long c : e.seg_launches) { sg.launches_per_step += c; }
+			sg.misses = 0;
+			me = sg.target;
 		}
-		rc = step_bail(ctx);	// the step ended before the recorded one did
-		if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+		else
+		{
+			rc = step_bail(ctx);	// the step ended before the predicted one did: now a recording, handled below
+			if(rc != NB200_OK || sg.mode == SG_OFF) { return rc; }
+		}
 	}
 	if(sg.mode == SG_CAPTURE)
 	{
 		if(sg.cur.empty()) { return NB200_OK; }
 		rc = step_close_segment(ctx);	// the last segment of the step
 		if(sg.mode == SG_OFF) { return rc; }
-		bool same = sg.cur.size() == sg.seq.size();
-		for(size_t k = 0; same && k < sg.cur.size(); ++k) { same = sg.cur[k].same(sg.seq[k]); }
-		if(same)
+		const bool as_predicted = step_same_sequence(sg.cur, sg.entries[static_cast<size_t>(sg.target)].seq);
+		me = as_predicted ? sg.target : step_find_or_add(ctx, sg.cur);
+		step_entry& e = sg.entries[static_cast<size_t>(me)];
+		if(!e.captured)
 		{
-			sg.mode = SG_REPLAY;
-			sg.pos = sg.seg = sg.seg_start = 0;
-			sg.launches_per_step = 0;
-			for(unsigned long long c : sg.seg_launches) { sg.launches_per_step += c; }
+			// whichever step this was, it has a graph now
+			e.execs.swap(sg.cap_execs);
+			e.seg_launches.swap(sg.cap_launches);
+			e.captured = true;
 		}
-		else
-		{
-			step_drop_graphs(ctx);
-			sg.seq.swap(sg.cur);	// a clean step all the same: try the next one against it
-			step_failure(ctx);
-		}
-		sg.cur.clear();
-		sg.clean = true;
-		return rc;
+		step_destroy_execs(ctx, sg.cap_execs);
+		sg.cap_launches.clear();
+		if(as_predicted) { sg.misses = 0; } else { step_miss(ctx); }
+		if(sg.mode == SG_OFF) { return rc; }
 	}
-	// SG_RECORD: a clean step (nothing host-visible inside except segment borders) becomes the candidate
-	if(sg.clean && !sg.cur.empty())
+	else if(sg.mode == SG_RECORD)
 	{
-		sg.seq.swap(sg.cur);
-		sg.mode = SG_CAPTURE;
-	}
-	else
-	{
-		sg.seq.clear();
+		// a clean step (nothing host-visible inside except segment borders) is filed; an unclean one breaks the chain
+		me = sg.clean ? step_find_or_add(ctx, sg.cur) : -1;
 	}
 	sg.cur.clear();
 	sg.clean = true;
+	sg.pos = sg.seg = sg.seg_start = 0;
+	if(sg.last >= 0 && me >= 0 && static_cast<size_t>(sg.last) < sg.entries.size())
+	{
+		sg.entries[static_cast<size_t>(sg.last)].next = me;
+	}
+	sg.last = me;
+	// the next step is predicted to be what followed this entry last time
+	sg.target = me >= 0 ? sg.entries[static_cast<size_t>(me)].next : -1;
+	if(sg.target < 0) { sg.mode = SG_RECORD; }
+	else { sg.mode = sg.entries[static_cast<size_t>(sg.target)].captured ? SG_REPLAY : SG_CAPTURE; }
 	return rc;
 }
 
-NB200_API int nb200_step_graph_stats(const nb200_ctx* ctx, unsigned long long out[4])
+NB200_API int nb200_step_graph_stats(const nb200_ctx* ctx, unsigned long long out[5])
 {
 	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
 	out[0] = ctx->sg->graph_launches;
 	out[1] = ctx->sg->bailouts;
 	out[2] = static_cast<unsigned long long>(ctx->sg->mode);
 	out[3] = ctx->sg->launches_per_step;
+	out[4] = ctx->sg->entries.size();
 	return NB200_OK;
 }
 
@@ -1949,11 +2070,11 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 		// deferral needs one stream that sees every call: single-shard contexts only (accepted and ignored otherwise)
 		const bool can = ctx->lanes.size() == 1 && ctx->nranks == 1;
 		step_graph& sg = *ctx->sg;
-		sg.seq.clear();
+		step_clear_table(ctx);
 		sg.cur.clear();
 		sg.clean = true;
-		sg.pos = 0;
-		sg.failures = 0;
+		sg.pos = sg.seg = sg.seg_start = 0;
+		sg.misses = 0;
 		sg.mode = (value != 0 && can) ? SG_RECORD : SG_OFF;
 	}
 	else if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }

@@ -311,10 +311,11 @@ class Engine:
         self._check(self.lib.nb200_step_boundary(self.ctx), "step_boundary")
 
     def step_graph_stats(self):
-        out = (C.c_ulonglong * 4)()
+        out = (C.c_ulonglong * 5)()
         self.lib.nb200_step_graph_stats(self.ctx, out)
         return dict(graph_launches=int(out[0]), bailouts=int(out[1]),
-                    state=("off", "record", "capture", "replay")[int(out[2])], launches_per_step=int(out[3]))
+                    state=("off", "record", "capture", "replay")[int(out[2])], launches_per_step=int(out[3]),
+                    distinct_steps=int(out[4]))
 
     def get_time(self):
         return self._time

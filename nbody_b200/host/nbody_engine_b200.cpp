@@ -561,7 +561,7 @@ void nbody_engine_b200::set_step_graph(bool active)
 	}
 }
 
-bool nbody_engine_b200::step_graph_stats(unsigned long long out[4]) const
+bool nbody_engine_b200::step_graph_stats(unsigned long long out[5]) const
 {
 	return d->m_ctx != nullptr && nb200_step_graph_stats(d->m_ctx, out) == NB200_OK;
 }
@@ -660,7 +660,7 @@ extern "C" __attribute__((visibility("default"))) void nbody_engine_b200_synchro
 	}
 }
 
-extern "C" __attribute__((visibility("default"))) int nbody_engine_b200_step_graph_stats(void* engine, unsigned long long out[4])
+extern "C" __attribute__((visibility("default"))) int nbody_engine_b200_step_graph_stats(void* engine, unsigned long long out[5])
 {
 	nbody_engine_b200* e = dynamic_cast<nbody_engine_b200*>(static_cast<nbody_engine*>(engine));
 	return (e != nullptr && e->step_graph_stats(out)) ? 0 : -1;

@@ -69,8 +69,8 @@ public:
 	//! Solver steps as CUDA graphs (factory parameter step_graph, default on): a step that repeats the previous one call for call
 	//! is replayed as one cudaGraphLaunch from advise_time(); results are those of the eager engine (include/nb200.h)
 	void set_step_graph(bool);
-	//! {graphs launched, replays abandoned, state, kernels per replayed step}
-	bool step_graph_stats(unsigned long long out[4]) const;
+	//! {graphs launched, replays abandoned, state of the next step, kernels in the step replayed last, distinct steps}
+	bool step_graph_stats(unsigned long long out[5]) const;
 	//! Device-side conservation sums of nbody_data::print_statistics (nbody_data.cpp:57-103) for a state vector:
 	//! out = {P[3], L[3], Ekin, Epot, mass centre[3]}; Epot (O(N^2), on the GPU) only when with_energy. False on error.
 	bool statistics(const memory* y, bool with_energy, double out[11]);

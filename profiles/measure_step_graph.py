@@ -45,7 +45,8 @@ def main():
                 s = R.Solver(lib, **p)
                 s.set_time_step(1e-9, 1e-3)
                 s.set_engine(e)
-                for _ in range(4):                           # allocation, record, capture, first replay
+                for _ in range(30 if n <= 16384 else 6):     # allocation, recording, capture, first replays (Bulirsch-Stoer and
+                    # Adams need a few outer steps until every sub-step / buffer rotation has its graph)
                     s.advise(1e-3)
                 ad.nbody_engine_b200_synchronize(h)
                 steps = 50 if n <= 16384 else 10
@@ -55,7 +56,7 @@ def main():
                     s.advise(1e-3)
                 ad.nbody_engine_b200_synchronize(h)
                 dt = (time.perf_counter() - t0) / steps
-                st = (C.c_ulonglong * 4)()
+                st = (C.c_ulonglong * 5)()
                 ad.nbody_engine_b200_step_graph_stats(h, st)
                 key = "graph" if graph else "eager"
                 row[key + "_s_per_step"] = dt
@@ -65,6 +66,7 @@ def main():
                     row["graphs_launched"] = int(st[0])
                     row["replays_abandoned"] = int(st[1])
                     row["state"] = ("off", "record", "capture", "replay")[int(st[2])]
+                    row["distinct_steps"] = int(st[4])
                 e.get_data(d)
                 states[graph] = d.export()[0].copy()
                 s.close()

@@ -89,12 +89,14 @@ def test_rk4_replayed_as_graphs_is_bit_identical(precision, kind, kw):
     assert np.array_equal(eager, graph)
     assert st0["state"] == "off" and st0["graph_launches"] == 0
     if kw.get("tree_build_rate"):
-        # the step number is part of the call (the tree is rebuilt every 4th step): steps differ, nothing is replayed
-        assert st1["graph_launches"] <= 9
+        # every 4th step rebuilds the tree, the others refresh it: two distinct steps, both end up with a graph, and a
+        # wrong guess between them is corrected at the first call (no replay is abandoned)
+        assert st1["distinct_steps"] == 2 and st1["bailouts"] == 0
+        assert st1["graph_launches"] >= steps - 4
     else:
-        assert st1["state"] == "replay"
-        assert st1["graph_launches"] == steps - 1          # step 1 recorded eagerly, steps 2.. as graphs
-        assert st1["bailouts"] == 0
+        assert st1["state"] == "replay" and st1["distinct_steps"] == 1
+        assert st1["graph_launches"] == steps - 2          # two steps recorded eagerly (the second confirms the first
+        assert st1["bailouts"] == 0                          # repeats), the third captured, the rest replayed
         assert st1["launches_per_step"] >= 8                  # direct at N = 2,048: 4 single-launch fcomputes + 4 state ops
         assert launches1 == launches0                        # the same kernels ran, only issued differently
 
@@ -106,7 +108,7 @@ def test_changed_step_size_falls_back_and_recaptures():
     graph, st, _, _ = run_rk4("f64", "direct", steps, graph=True, dts=dts)
     assert np.array_equal(eager, graph)
     assert st["bailouts"] == 1                               # step 6: the first fmadd carries another coefficient
-    assert st["state"] == "replay" and st["graph_launches"] >= 8
+    assert st["state"] == "replay" and st["graph_launches"] >= 7 and st["distinct_steps"] == 2
 
 
 def test_read_in_the_middle_of_a_replayed_step():
@@ -118,13 +120,28 @@ def test_read_in_the_middle_of_a_replayed_step():
     assert st["bailouts"] == 1
 
 
-def test_every_step_different_gives_up_quietly():
+def test_every_step_different_is_never_captured():
     steps = 14
     dts = [1e-3 * (1 + 0.01 * i) for i in range(steps)]
+    eager, _, launches0, _ = run_rk4("f64", "direct", steps, graph=False, dts=dts)
+    graph, st, launches1, _ = run_rk4("f64", "direct", steps, graph=True, dts=dts)
+    assert np.array_equal(eager, graph)
+    # nothing ever repeats, so nothing is predicted: every step runs eagerly, no capture is wasted
+    assert st["state"] == "record" and st["graph_launches"] == 0 and st["bailouts"] == 0
+    assert st["distinct_steps"] == steps and launches0 == launches1
+
+
+def test_alternating_step_sizes_get_one_graph_each():
+    """A caller that alternates between two steps (here: two step sizes; Bulirsch-Stoer's sub-steps and Adams' rotating
+    history buffers are the reference's cases): both are filed, both get a graph, and from then on every step is one
+    graph launch."""
+    steps = 16
+    dts = [1e-3 if i % 2 == 0 else 5e-4 for i in range(steps)]
     eager, _, _, _ = run_rk4("f64", "direct", steps, graph=False, dts=dts)
     graph, st, _, _ = run_rk4("f64", "direct", steps, graph=True, dts=dts)
     assert np.array_equal(eager, graph)
-    assert st["state"] == "off"                              # after a few fruitless captures the library stays eager
+    assert st["distinct_steps"] == 2 and st["state"] == "replay"
+    assert st["graph_launches"] >= steps - 6 and st["bailouts"] <= 1
 
 
 class Rk4Err(Rk4):
@@ -191,7 +208,7 @@ def test_fmaxabs_inside_the_step_splits_the_graph_in_two():
     assert np.array_equal(eager, graph)
     assert err0 == err1 and all(v > 0 for v in err0)         # the reduction saw the finished stages every time
     assert st["state"] == "replay" and st["bailouts"] == 0
-    assert st["graph_launches"] == 2 * (steps - 1)           # two segments per step: before and after the border
+    assert st["graph_launches"] == 2 * (steps - 2)           # two segments per step: before and after the border
     assert launches0 == launches1
 
 
@@ -237,7 +254,7 @@ def test_reference_solver_golden_with_step_graphs(ref64, adapter, name, params):
         s.set_engine(e)
         assert s.run(d, 0.3) == 0
         e.get_data(d)
-        out = (C.c_ulonglong * 4)()
+        out = (C.c_ulonglong * 5)()
         adapter.nbody_engine_b200_step_graph_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
         assert adapter.nbody_engine_b200_step_graph_stats(e.h, out) == 0
         expected = R.Data(ref64).load(golden_path(name + ".txt"))
@@ -252,6 +269,9 @@ def test_reference_solver_golden_with_step_graphs(ref64, adapter, name, params):
     if name in ("rkf", "rkdp", "rkfeagin14"):
         # embedded tables read the error norm back in every step: replayed as two graphs per step around the border
         assert states[1][1][0] >= 4, "embedded solver was not replayed: %r" % (states[1][1],)
+    if name in ("adams5", "bulirsch-stoer"):
+        # periodic patterns (rotating history buffers; sub-steps of several sizes): several distinct steps, some replayed
+        assert states[1][1][4] >= 2
 
 
 # ---- body arrays <-> state vector -----------------------------------------------------------------------------------
