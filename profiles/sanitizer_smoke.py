@@ -55,3 +55,22 @@ for dev in ("0", "0,0"):               # body transposes + solver steps replayed
             e.advise_time(1e-3)
         p, v = e.get_bodies()
         print("bodies + step graph", dev, e.step_graph_stats(), err, float(np.abs(p).max()))
+n = 2048
+y = rng.uniform(-50, 50, 6*n); m = rng.uniform(0.1, 2, n)
+for prec in ("f64", "f32"):            # single-launch kernel for small systems; 2-warp / 1-warp symmetric tiles of 256 bodies
+    for opts in ((), (("direct_symmetric", 1), ("direct_sym_tile", 256)), (("direct_symmetric", 1), ("direct_sym_tile", 512))):
+        with Engine(precision=prec) as e:
+            for k, v in opts: e.set_option(k, v)
+            assert e.init(y, m)
+            f = e.create_buffer(e.get_y().size())
+            e.fcompute(0, e.get_y(), f)
+            print(prec, opts, "path", e.last_direct_path(), e.fmaxabs(f))
+with Engine() as e:                    # step table: two alternating steps, both captured and replayed
+    assert e.init(y, m)
+    e.set_option("step_graph", 1)
+    dy = e.create_buffer(e.get_y().size())
+    for i in range(10):
+        e.fcompute(0, e.get_y(), dy)
+        e.fmadd_inplace(e.get_y(), dy, 1e-3 if i % 2 else 5e-4)
+        e.advise_time(1e-3)
+    print("alternating steps", e.step_graph_stats(), e.fmaxabs(e.get_y()))
