@@ -451,10 +451,22 @@ int step_retarget(nb200_ctx* ctx, const step_op& op)
 	sg.cur.clear();
 	if(step_begin_segment(ctx) != NB200_OK) { return 0; }
 	sg.mode = SG_CAPTURE;
-	if(step_issue_range(ctx, have, 0, upto) != NB200_OK) { return 0; }
+	const int issued = step_issue_range(ctx, have, 0, upto);
 	sg.cur.assign(have.begin(), have.begin() + static_cast<std::ptrdiff_t>(upto));
-	sg.target = uncaptured;
 	sg.pos = sg.seg = sg.seg_start = 0;
+	if(issued != NB200_OK)
+	{
+		// a call that was accepted before fails now: run what was captured and carry on eagerly (the error shows up
+		// again when the caller's own call is issued)
+		step_close_segment(ctx);
+		step_destroy_execs(ctx, sg.cap_execs);
+		sg.cap_launches.clear();
+		if(sg.mode != SG_OFF) { sg.mode = SG_RECORD; }
+		sg.target = -1;
+		sg.clean = false;
+		return 2;
+	}
+	sg.target = uncaptured;
 	return 2;
 }
 
