@@ -854,7 +854,7 @@ NB200_API int nb200_set_bodies(nb200_ctx* ctx, size_t n, const nb200_real* mass)
 	ctx->n = n;
 	ctx->n_shard = n / static_cast<size_t>(ctx->nshards);
 	ctx->n_pad = (n + NB200_DIRECT_TILE - 1) / NB200_DIRECT_TILE * NB200_DIRECT_TILE;
-	ctx->n_alloc = (n + 8191) / 8192 * 8192;	// room for the zero-mass padding of the largest symmetric tile edge
+	ctx->n_alloc = (n + 8191) / 8192 * 8192 + 8192;	// room for the zero-mass padding of a last tile of any edge <= 8192
 	for(auto& l : ctx->lanes)
 	{
 		CU(ctx, cudaSetDevice(l.dev));
@@ -1202,7 +1202,7 @@ int sym_tile_edge(const nb200_ctx* ctx)
 		edge = 256;
 		while(edge * 2 <= static_cast<long long>(ctx->n / 128) && edge < 8192) { edge *= 2; }
 	}
-	// a power of two in [256, 8192]: the zero-mass padding of the packed sources (n_alloc) covers whole tiles of any such edge
+	// a power of two in [256, 8192]
 	if(edge > 8192 || edge < 256 || (edge & (edge - 1)) != 0) { return 0; }
 	if(ctx->opt_sym_shape == NB200_SYM_DEFAULT_SHAPE)
 	{

@@ -105,7 +105,9 @@ __device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_r
 // shuffled right after its own I pairs, so that the shuffles overlap the next body's arithmetic (192 instead of 230
 // registers) -- measured 5 % SLOWER at N = 1M (901 vs 855 ms); kept selectable (direct_sym_shape 6) for A/B runs.
 // Also measured and rejected: two CTAs per SM with <= 128 registers and tile edge 4096 (<2,2> 967 ms, <4,1> 903 ms,
-// <4,2> with 68 bytes of spills 903 ms); tile edge 4096 with this kernel: 846 ms, but twice the partial-sum scratch.
+// <4,2> with 68 bytes of spills 903 ms); 12 warps per SM at 168 registers, no spills, tiles of 3072 / 6144 (1.12e12
+// pairs/s, with the early shuffles 1.20e12, against 1.285e12 here): fewer warps with more registers each win;
+// tile edge 4096 with this kernel: 846 ms, but twice the partial-sum scratch.
 // WARPS: warps per CTA. A tile needs T / (32 I) row blocks; with fewer than 8 of them (small tiles for small N) the
 // CTA shrinks instead of leaving warps idle, and several CTAs share an SM (230 registers x 128 threads fit twice).
 template<int I, int J, bool LATE_SHUFFLES = true, int WARPS = NB200_SYM_WARPS>
