@@ -2093,6 +2093,7 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }
 	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = automatic, 1 = thread per target, 2 / 4 = targets per lane, 32 = one per lane
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
+	else if(strcmp(name, "walk_lpt") == 0) { ctx->opt_walk_lpt = value; }	// -1 automatic, 0 off, 1 on
 	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; }	// -1 auto, 0 off, 1 on
 	else if(strcmp(name, "direct_small") == 0) { ctx->opt_direct_small = value; }	// -1 auto (N <= 4096), 0 off, 1 on
 	else if(strcmp(name, "direct_sym_tile") == 0) { ctx->opt_sym_tile = value; }

@@ -79,6 +79,16 @@ struct bh_state
 	int*	leaf_pos = nullptr;	// [n] leaf position of every body (inverse of body_n[n..2n))
 	real*	acc_all = nullptr;	// [shards][3][n_shard] accelerations in leaf order
 	bool	have_tree = false;
+	// longest-walk-first launch order of the walk's CTAs (see bh_walk_warp_multi): cost of every CTA in the last walk,
+	// and the permutation the next walk is launched in
+	unsigned*	lpt_cost = nullptr;		// [ctas] clock cycles of the CTA's first warp
+	unsigned*	lpt_cost_sorted = nullptr;
+	int*		lpt_iota = nullptr;		// 0, 1, 2, ...
+	int*		lpt_order = nullptr;	// CTA indices, most expensive first
+	void*		lpt_tmp = nullptr;
+	size_t		lpt_tmp_bytes = 0;
+	int			lpt_ctas = 0;			// CTAs the arrays are sized for
+	bool		lpt_have_order = false;
 };
 
 static void bh_free(bh_state* s)
@@ -86,7 +96,7 @@ static void bh_free(bh_state* s)
 	if(s == nullptr) { return; }
 	void* ptrs[] = {s->xyzr, s->nmass, s->bmin, s->bmax, s->body_n, s->keys_in, s->keys_out, s->iota, s->ord[0], s->ord[1],
 					s->ord[2], s->ord_tmp[0], s->ord_tmp[1], s->ord_tmp[2], s->side, s->blk, s->cub_tmp, s->leaf_pos,
-					s->acc_all};
+					s->acc_all, s->lpt_cost, s->lpt_cost_sorted, s->lpt_iota, s->lpt_order, s->lpt_tmp};
 	for(void* p : ptrs)
 	{
 		if(p != nullptr) { cudaFree(p); }
@@ -526,13 +536,25 @@ __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const no
 // the votes and the loop control of a visit are shared by TPL acceptance tests per lane instead of one. Each target
 // still accepts exactly the nodes of its own stackless traversal, in the same order: results are bit-identical to
 // bh_walk_warp (tested). Target k of lane l is leaf base + 32 k + l, so every load and store stays coalesced.
+//
+// Launch order. Walks differ in length (targets in dense regions open more nodes), and the last, partly filled wave of
+// CTAs sets the kernel's end -- noticeably once a GPU has only a few waves of them (4M bodies over 8 GPUs: 1.7 waves).
+// cta_cost, if given, receives the clock cycles each CTA's first warp took; cta_order, if given, is a permutation of
+// the CTA indices, and the host passes last step's costs sorted in descending order: the longest walks start first and
+// the short ones fill the end (longest-processing-time-first). Which CTA computes which targets does not change what is
+// computed: results stay bit-identical.
 template<int TPL, bool STATS, int MINB>
 __global__ void __launch_bounds__(128, MINB) bh_walk_warp_multi(const node4* __restrict__ xyzr, const real* __restrict__ nmass,
 														 const int* __restrict__ body_n, real* __restrict__ acc_leaf, int3 deal,
 														 const real* __restrict__ y, real* __restrict__ f, int n, int n_targets,
-														 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats)
+														 size_t n_shard, int shard_first, unsigned long long* __restrict__ stats,
+														 const int* __restrict__ cta_order, unsigned* __restrict__ cta_cost)
 {
-	const int	warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	// the cost of a CTA is the time its first thread spends here; the start time waits in shared memory so that the walk
+	// loop, which has no register to spare at 64 per thread, carries nothing for it
+	__shared__ unsigned t_begin;
+	if(cta_cost != nullptr && threadIdx.x == 0) { t_begin = static_cast<unsigned>(clock64()); }
+	const int	warp = ((cta_order != nullptr ? cta_order[blockIdx.x] : static_cast<int>(blockIdx.x)) * blockDim.x + threadIdx.x) >> 5;
 	const int	lane = threadIdx.x & 31;
 	const int	tree_size = 2 * n;
 	int			t[TPL], leaf[TPL], resume[TPL];
@@ -588,6 +610,10 @@ __global__ void __launch_bounds__(128, MINB) bh_walk_warp_multi(const node4* __r
 		}
 		curr = (__any_sync(0xffffffffu, any_open) && child < tree_size) ? child : skip;
 	} while(curr != 1);
+	if(cta_cost != nullptr && threadIdx.x == 0)
+	{
+		cta_cost[cta_order != nullptr ? cta_order[blockIdx.x] : static_cast<int>(blockIdx.x)] = static_cast<unsigned>(clock64()) - t_begin;
+	}
 #pragma unroll
 	for(int k = 0; k < TPL; ++k)
 	{
@@ -745,6 +771,42 @@ static int bh_update_geometry(nb200_ctx* ctx, nb200_lane& l, int& launches, std:
 	return NB200_OK;
 }
 
+__global__ void __launch_bounds__(256) bh_iota(int* __restrict__ out, int count)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < count) { out[i] = i; }
+}
+
+// Arrays of the longest-walk-first launch order, for `ctas` CTAs
+static int bh_lpt_alloc(nb200_lane& l, bh_state* s, int ctas, int& launches, std::string& err)
+{
+	if(s->lpt_ctas == ctas) { return NB200_OK; }
+	void* old[] = {s->lpt_cost, s->lpt_cost_sorted, s->lpt_iota, s->lpt_order, s->lpt_tmp};
+	for(void* p : old) { if(p != nullptr) { cudaFree(p); } }
+	s->lpt_cost = s->lpt_cost_sorted = nullptr;
+	s->lpt_iota = s->lpt_order = nullptr;
+	s->lpt_tmp = nullptr;
+	s->lpt_ctas = 0;
+	s->lpt_have_order = false;
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, s->lpt_cost, s->lpt_cost_sorted, s->lpt_iota, s->lpt_order, ctas);
+	const size_t count = static_cast<size_t>(ctas);
+	if(cudaMalloc(&s->lpt_cost, count * sizeof(unsigned)) != cudaSuccess || cudaMalloc(&s->lpt_cost_sorted, count * sizeof(unsigned)) != cudaSuccess ||
+	   cudaMalloc(&s->lpt_iota, count * sizeof(int)) != cudaSuccess || cudaMalloc(&s->lpt_order, count * sizeof(int)) != cudaSuccess ||
+	   cudaMalloc(&s->lpt_tmp, std::max<size_t>(bytes, 16)) != cudaSuccess)
+	{
+		cudaGetLastError();
+		err = "walk order allocation failed";
+		return NB200_ERR_ALLOC;
+	}
+	s->lpt_tmp_bytes = bytes;
+	s->lpt_ctas = ctas;
+	bh_iota<<<(ctas + 255) / 256, 256, 0, l.stream>>>(s->lpt_iota, ctas);
+	++launches;
+	BH_CU(cudaGetLastError());
+	return NB200_OK;
+}
+
 static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, size_t step, int& launches, std::string& err)
 {
 	int rc = bh_alloc(ctx, l, err);
@@ -794,10 +856,33 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 		// FP32 647 -> 438 ms; four: 754 / 439 ms (114 registers, a quarter of the warp slots)
 		const int		tpl = ctx->opt_walk_mode == 4 ? 4 : 2;
 		const unsigned	mgrid = static_cast<unsigned>((n_targets + 128 * tpl - 1) / (128 * tpl));
-		if(tpl == 2 && stats != nullptr) { bh_walk_warp_multi<2, true, 8><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
-		else if(tpl == 2) { bh_walk_warp_multi<2, false, 8><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
-		else if(stats != nullptr) { bh_walk_warp_multi<4, true, 4><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
-		else { bh_walk_warp_multi<4, false, 4><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats); }
+		// longest-walk-first order from the previous walk's costs. Automatic for 1024..4096 CTAs (262,144..1,048,576
+		// targets per GPU, e.g. 4M bodies over 4 or 8 GPUs): below that the walk is short and the sort's launches cost more
+		// than the tail they remove; above it there are many waves, the tail is a small share, and launching neighbours
+		// in the kd order together (shared upper-tree nodes in L1/L2) is worth more. One B200, ratio 10: N = 524,288
+		// 57.4 -> 50.8 ms, N = 1M 130.3 -> 125.0 ms, N = 4M 2.5 % slower
+		const bool		lpt = tpl == 2 && (ctx->opt_walk_lpt > 0 || (ctx->opt_walk_lpt < 0 && mgrid >= 1024 && mgrid <= 4096));
+		const int*		order = nullptr;
+		unsigned*		cost = nullptr;
+		if(lpt)
+		{
+			rc = bh_lpt_alloc(l, s, static_cast<int>(mgrid), launches, err);
+			if(rc != NB200_OK) { return rc; }
+			order = s->lpt_have_order ? s->lpt_order : nullptr;
+			cost = s->lpt_cost;
+		}
+		if(tpl == 2 && stats != nullptr) { bh_walk_warp_multi<2, true, 8><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats, order, cost); }
+		else if(tpl == 2) { bh_walk_warp_multi<2, false, 8><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats, order, cost); }
+		else if(stats != nullptr) { bh_walk_warp_multi<4, true, 4><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats, nullptr, nullptr); }
+		else { bh_walk_warp_multi<4, false, 4><<<mgrid, 128, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats, nullptr, nullptr); }
+		if(lpt)
+		{
+			// next walk's order: this walk's costs, descending (stream-ordered after the walk; ~20 us at 16384 CTAs)
+			size_t bytes = s->lpt_tmp_bytes;
+			BH_CU(cub::DeviceRadixSort::SortPairsDescending(s->lpt_tmp, bytes, s->lpt_cost, s->lpt_cost_sorted, s->lpt_iota, s->lpt_order,
+															static_cast<int>(mgrid), 0, 32, l.stream));
+			s->lpt_have_order = true;
+		}
 	}
 	else if(stats != nullptr)
 	{

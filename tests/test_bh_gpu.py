@@ -11,13 +11,16 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def run_bh(y, m, ratio, precision="f64", devices="0", layout="heap_stackless", rate=0, walk_mode=0, steps=1, stats=False):
+def run_bh(y, m, ratio, precision="f64", devices="0", layout="heap_stackless", rate=0, walk_mode=0, steps=1, stats=False,
+           options=()):
     """Returns list of f per step (y *= 0.99 between steps, like test_fcompute), the exported tree and stats."""
     from nbody_b200 import Engine
     out = []
     with Engine(precision=precision, devices=devices, kind="bh", distance_to_node_radius_ratio=ratio,
                 tree_layout=layout, tree_build_rate=rate) as e:
         e.set_option("walk_mode", walk_mode)
+        for k, v in options:
+            e.set_option(k, v)
         assert e.init(y, m)
         if stats:
             e.bh_walk_stats(True)
@@ -86,6 +89,18 @@ def test_bh_several_targets_per_lane_bit_identical(precision, n, ratio, devices)
         (b,), _, sb = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=mode, stats=True)
         assert np.array_equal(a, b), "walk_mode %d" % mode
         assert sa == sb
+
+
+@pytest.mark.parametrize("devices", ["0", "0,0"])
+def test_bh_longest_walk_first_order_changes_nothing(devices):
+    """walk_lpt: from the second walk on the CTAs are launched most-expensive-first (costs of the previous walk, sorted
+    on the device). Which CTA walks which leaves does not change any target's traversal: bit-identical forces."""
+    y, m = universe(65536)
+    a, _, sa = run_bh(y, m, 10.0, devices=devices, steps=3, stats=True, options=(("walk_lpt", 0),))
+    b, _, sb = run_bh(y, m, 10.0, devices=devices, steps=3, stats=True, options=(("walk_lpt", 1),))
+    assert sa == sb
+    for fa, fb in zip(a, b):
+        assert np.array_equal(fa, fb)
 
 
 def test_bh_counts_match_oracle(oracle64):
