@@ -217,7 +217,8 @@ int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms);
 int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s);
 /* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "direct_symmetric" / "direct_small" (-1 automatic,
  * 0 off, 1 on), "direct_sym_tile" (power of two, 256..8192), "walk_mode" (0 = automatic: warp-coherent walk
- * with two targets per lane; 1 = one thread per target; 2 / 4 = targets per lane; 32 = one target per lane), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
+ * with two targets per lane; 1 = one thread per target; 2 / 4 = targets per lane; 32 = one target per lane), "walk_lpt" (walk CTAs launched longest
+ * walk first: -1 automatic, 0 off, 1 on), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
 int nb200_set_option(nb200_ctx* ctx, const char* name, long long value);
 
 #ifdef __cplusplus
