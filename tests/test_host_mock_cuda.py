@@ -47,6 +47,20 @@ def test_host_logic_scenarios_under_the_mock_runtime(mock_runtime):
     assert "all host-logic scenarios passed" in res.stdout
 
 
+def test_every_reference_solver_is_replayed_under_the_mock_runtime(mock_runtime):
+    """The reference's own solver classes on the C++ adapter: euler ... rkfeagin14 (one table entry), Adams (its history
+    buffers rotate: 10 entries), Bulirsch-Stoer (12 distinct sub-steps) all end up as graph launches only."""
+    from nbody_b200 import build
+    from oracle import refharness as R
+    if not R.available("f64") or not os.path.exists(build.adapter_path("f64")):
+        pytest.skip("needs oracle/_ref and the C++ adapter (built where /root/reference is mounted)")
+    env = dict(os.environ, LD_PRELOAD=mock_runtime, NBREF_QUIET="1")
+    res = subprocess.run([sys.executable, os.path.join(HERE, "drive_adapter.py"), mock_runtime], env=env, capture_output=True,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "all reference solvers replayed" in res.stdout and res.stdout.count("ok ") == 19, res.stdout
+
+
 def test_without_the_mock_there_is_still_no_device(mock_runtime):
     """The stand-in only exists inside the subprocess above: a plain process on this machine gets no context."""
     code = ("import sys; sys.path.insert(0, %r)\n"
