@@ -283,7 +283,71 @@ def scenario_tree_build_rate():
     print("ok tree_build_rate")
 
 
+def scenario_direct_path_selection():
+    """Which kernel family nb200_fcompute_direct picks (nb200_last_direct_path: -1 single launch, 0 ordered pairs, else the
+    symmetric tile edge) and how many kernels that is, by N, precision, shard count and tunables."""
+    cases = [("f64", "0", 16, (), -1, 1), ("f64", "0", 2048, (), -1, 1), ("f64", "0", 4096, (), -1, 1),
+             ("f64", "0", 4160, (), 0, 3),                                       # pack + pairs + reduce
+             ("f64", "0", 8192, (), 256, 4), ("f64", "0", 32768, (), 256, 4),  # pack + tiles + reduce + finish
+             ("f64", "0", 65536, (), 512, 4), ("f64", "0", 131072, (), 1024, 4), ("f64", "0", 262144, (), 2048, 4),
+             ("f32", "0", 8192, (), 0, 3), ("f32", "0", 16384, (), 256, 4), ("f32", "0", 65536, (), 512, 4),
+             ("f64", "0,0", 2048, (), 0, 6),                                    # several shards: the tiled path
+             ("f64", "0,0", 65536, (), 512, 10),                                # + peer sum of the partials, per lane
+             ("f64", "0", 2048, (("direct_small", 0),), 0, 3), ("f64", "0", 2048, (("direct_symmetric", 0),), 0, 3),
+             ("f64", "0", 65536, (("direct_symmetric", 0),), 0, 3), ("f64", "0", 2048, (("direct_symmetric", 1),), 256, 4),
+             ("f64", "0", 6000, (("direct_small", 1),), -1, 1),
+             ("f64", "0", 65536, (("direct_sym_tile", 1536),), 0, 3)]           # not a power of two: ordered pairs
+    for precision, devices, n, opts, want_path, want_launches in cases:
+        y, m = system(n)
+        with Engine(precision=precision, devices=devices) as e:
+            for k, v in opts:
+                e.set_option(k, v)
+            assert e.init(y, m)
+            f = e.create_buffer(e.get_y().size())
+            e.fcompute(0.0, e.get_y(), f)                                       # first call: scratch allocation
+            before = e.launch_count()
+            with Delta() as c:
+                e.fcompute(0.0, e.get_y(), f)
+            got = (e.last_direct_path(), e.launch_count() - before)
+            assert got == (want_path, want_launches) and c.d[EAGER] == want_launches, (precision, devices, n, opts, got)
+    print("ok direct_path_selection")
+
+
+def scenario_bodies_and_statistics_are_host_visible():
+    y, m = system(256)
+    n = m.size
+    pos, vel = np.ascontiguousarray(y.reshape(6, n)[:3].T), np.ascontiguousarray(y.reshape(6, n)[3:].T)
+    for devices, lanes in (("0", 1), ("0,0,0,0", 4)):
+        with Engine(devices=devices) as e:
+            with Delta() as c:
+                assert e.init_bodies(pos, vel, m)
+            assert c.d[EAGER] == lanes and c.d[COPIES] >= 2 * lanes             # two uploads + one transpose kernel per lane
+            with Delta() as c:
+                assert e.get_bodies() is not None
+            assert c.d[EAGER] == lanes and c.d[COPIES] == 2 * lanes             # one transpose kernel + two downloads per lane
+            assert e.host_register(pos) == 0 and e.host_unregister(pos) == 0
+            small = e.create_buffer(64)
+            assert e.lib.nb200_read_bodies(e.ctx, small.handle, pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p)) == -1
+            assert e.lib.nb200_read_bodies(e.ctx, e.get_y().handle, None, None) == -1
+    with Engine() as e:
+        assert e.init(y, m)
+        e.set_option("step_graph", 1)
+        dy = e.create_buffer(y.nbytes)
+        for _ in range(5):
+            e.fcompute(0.0, e.get_y(), dy)
+            e.fmadd_inplace(e.get_y(), dy, 1e-3)
+            e.advise_time(1e-3)
+        assert e.step_graph_stats()["state"] == "replay"
+        e.fcompute(0.0, e.get_y(), dy)
+        with Delta() as c:
+            e.statistics(with_energy=False)                                     # host-visible: the accepted fcompute runs first
+        assert c.d[EAGER] >= 2 and e.step_graph_stats()["bailouts"] == 1
+    print("ok bodies_and_statistics_are_host_visible")
+
+
 if __name__ == "__main__":
+    scenario_direct_path_selection()
+    scenario_bodies_and_statistics_are_host_visible()
     scenario_tree_build_rate()
     scenario_buffers_and_shards()
     scenario_fixed_step_replay()

@@ -42,7 +42,8 @@ def test_host_logic_scenarios_under_the_mock_runtime(mock_runtime):
                          text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     for name in ("buffers_and_shards", "fixed_step_replay", "deferral_is_real", "error_norm_border", "read_in_the_middle",
-                 "periodic_patterns", "never_repeating_and_table_limit", "buffers_change_empties_the_table", "tree_build_rate"):
+                 "periodic_patterns", "never_repeating_and_table_limit", "buffers_change_empties_the_table", "tree_build_rate",
+                 "direct_path_selection", "bodies_and_statistics_are_host_visible"):
         assert "ok " + name in res.stdout, res.stdout
     assert "all host-logic scenarios passed" in res.stdout
 
