@@ -308,3 +308,25 @@ def test_bodies_round_trip(precision, devices, n):
         assert e.get_bodies(np.zeros((n, 2), dtype=dtype), v2) is None
         e.free_buffer(small)
         e.free_buffer(f)
+
+
+def test_barnes_hut_with_launch_order_inside_the_graph():
+    """N = 262,144 Barnes-Hut euler steps: the walk's longest-walk-first launch order (costs written by the walk, sorted on
+    the device, read by the next walk) lives inside the replayed graph. Bit-identical to eager issue with natural order."""
+    from nbody_b200 import Engine
+    from util import universe
+    y, m = universe(262144)
+    out = {}
+    for graph, lpt in ((0, 0), (1, -1)):
+        with Engine(kind="bh", distance_to_node_radius_ratio=2.0) as e:
+            e.set_option("walk_lpt", lpt)
+            assert e.init(y, m)
+            e.set_option("step_graph", graph)
+            dy = e.create_buffer(e.get_y().size())
+            for _ in range(6):
+                e.fcompute(e.get_time(), e.get_y(), dy)
+                e.fmadd_inplace(e.get_y(), dy, 1e-3)
+                e.advise_time(1e-3)
+            out[graph] = (e.read_buffer(e.get_y()), e.step_graph_stats())
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[1][1]["state"] == "replay" and out[1][1]["graph_launches"] == 4 and out[1][1]["bailouts"] == 0
