@@ -115,6 +115,11 @@ int nb200_free(nb200_ctx* ctx, nb200_buf* buf);       /* NULL is a no-op */
 size_t nb200_size(const nb200_buf* buf);              /* logical size in bytes */
 int nb200_write(nb200_ctx* ctx, nb200_buf* dst, const void* host_src);
 int nb200_read(nb200_ctx* ctx, void* host_dst, const nb200_buf* src);
+/* Like nb200_read, but only the columns this process owns are written into the
+ * full-layout host array (nranks > 1: no gather, D2H of the own shard only; the
+ * other columns of host_dst are left untouched). With one rank it equals
+ * nb200_read. For callers that keep per-rank output, e.g. a sharded dump. */
+int nb200_read_local(nb200_ctx* ctx, void* host_dst, const nb200_buf* src);
 int nb200_copy(nb200_ctx* ctx, nb200_buf* a, const nb200_buf* b);   /* sizes must match */
 int nb200_fill(nb200_ctx* ctx, nb200_buf* a, nb200_real value);
 /* Raw device pointer + element count of one lane's shard (zero-copy interop

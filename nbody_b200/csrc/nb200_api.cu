@@ -672,6 +672,26 @@ NB200_API int nb200_read(nb200_ctx* ctx, void* host, const nb200_buf* src)
 		CU(ctx, cudaStreamSynchronize(l.stream));
 		return NB200_OK;
 	}
+	return nb200_read_local(ctx, host, src);
+}
+
+NB200_API int nb200_read_local(nb200_ctx* ctx, void* host, const nb200_buf* src)
+{
+	if(ctx == nullptr) { return NB200_ERR_ARG; }
+	if(!valid(ctx, src)) { return fail(ctx, NB200_ERR_ARG, "read: src is not a buffer of this context"); }
+	if(host == nullptr) { return fail(ctx, NB200_ERR_ARG, "read: NULL destination"); }
+	step_break(ctx);
+	if(!src->sharded)
+	{
+		nb200_lane& l = ctx->lanes[0];
+		CU(ctx, cudaSetDevice(l.dev));
+		if(src->bytes != 0)
+		{
+			CU(ctx, cudaMemcpyAsync(host, src->dptr[0], src->bytes, cudaMemcpyDeviceToHost, l.stream));
+		}
+		CU(ctx, cudaStreamSynchronize(l.stream));
+		return NB200_OK;
+	}
 	for(size_t i = 0; i < ctx->lanes.size(); ++i)
 	{
 		nb200_lane& l = ctx->lanes[i];

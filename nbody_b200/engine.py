@@ -65,6 +65,7 @@ def load_library(precision="f64"):
     sig("nb200_size", sz, vp)
     sig("nb200_write", i32, vp, vp, vp)
     sig("nb200_read", i32, vp, vp, vp)
+    sig("nb200_read_local", i32, vp, vp, vp)
     sig("nb200_copy", i32, vp, vp, vp)
     sig("nb200_fill", i32, vp, vp, real)
     sig("nb200_lane_ptr", i32, vp, vp, i32, P(vp), P(sz))
@@ -393,6 +394,12 @@ class Engine:
         h = self._h(src, "read_buffer", "src")
         if h is not None:
             self._check(self.lib.nb200_read(self.ctx, C.c_void_p(host), h), "read_buffer")
+
+    def read_local_into(self, host, src):
+        """Only this process's shard columns of `src` into the full-layout host array (no gather across ranks)."""
+        h = self._h(src, "read_buffer", "src")
+        if h is not None:
+            self._check(self.lib.nb200_read_local(self.ctx, C.c_void_p(host), h), "read_buffer")
 
     def write_from(self, dst, host):
         h = self._h(dst, "write_buffer", "dst")

@@ -20,7 +20,7 @@ def build(force=False):
     """gcc the restatement (and, where /root/reference is mounted, the reference itself)."""
     targets = ["oracle"]
     if os.path.isdir("/root/reference/nbody"):
-        targets += ["ref", "ref_cuda"]
+        targets += ["ref", "ref_v4", "ref_cuda"]
     cmd = ["make", "-C", _HERE, "-j8"] + (["-B"] if force else []) + targets
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
 

@@ -14,12 +14,29 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBS = {}
 
 
-def lib_path(precision="f64"):
-    return os.path.join(_HERE, "_ref", "libnbref_%s.so" % precision)
+def lib_path(precision="f64", variant=""):
+    return os.path.join(_HERE, "_ref", "libnbref_%s%s.so" % (precision, "_" + variant if variant else ""))
 
 
-def available(precision="f64"):
-    return os.path.exists(lib_path(precision))
+def available(precision="f64", variant=""):
+    return os.path.exists(lib_path(precision, variant))
+
+
+def host_variant(precision="f64"):
+    """The build of the reference that matches this host best: "v4" (-march=x86-64-v4, AVX-512) where the CPU has
+    avx512f/bw/cd/dq/vl and that build exists, else "" (-march=x86-64-v3). The reference itself builds with
+    -march=native (pri/vectorize.pri:4); these two fixed levels are what can be prebuilt and shipped."""
+    if precision != "f64" or not available(precision, "v4"):
+        return ""
+    try:
+        flags = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = set(line.split(":", 1)[1].split())
+                break
+    except OSError:
+        return ""
+    return "v4" if {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags else ""
 
 
 def _sig(lib, name, restype, *argtypes):
@@ -29,13 +46,14 @@ def _sig(lib, name, restype, *argtypes):
     return fn
 
 
-def load(precision="f64"):
+def load(precision="f64", variant=""):
     """Load (once) and type the nbref_* entry points. RTLD_LOCAL: the f64 and f32
     builds define the same C++ symbols with different layouts and must not see
     each other; the nb200 adapter library links its libnbref_* explicitly."""
-    if precision in _LIBS:
-        return _LIBS[precision]
-    lib = C.CDLL(lib_path(precision), mode=C.RTLD_LOCAL)
+    key = precision + variant
+    if key in _LIBS:
+        return _LIBS[key]
+    lib = C.CDLL(lib_path(precision, variant), mode=C.RTLD_LOCAL)
     vp, sz, dbl, cs, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_char_p, C.c_int
     _sig(lib, "nbref_coord_size", i32)
     _sig(lib, "nbref_max_threads", i32)
@@ -105,7 +123,8 @@ def load(precision="f64"):
     lib.precision = precision
     lib.dtype = np.float64 if precision == "f64" else np.float32
     assert lib.nbref_coord_size() == np.dtype(lib.dtype).itemsize
-    _LIBS[precision] = lib
+    lib.variant = variant
+    _LIBS[key] = lib
     return lib
 
 
