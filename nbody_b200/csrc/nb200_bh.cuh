@@ -382,6 +382,19 @@ __device__ __forceinline__ void store_f(const real* __restrict__ y, real* __rest
 	f[5 * n_shard + li] = az;
 }
 
+// |me - node|^2 of the acceptance test, with the rounding the reference's (v1 - cm).norm() gets from gcc -O3 (and that
+// nvcc's own contraction of dx*dx + dy*dy + dz*dz produces): fma(dz, dz, fma(dx, dx, dy*dy)). Written out so that every
+// walk -- scalar, packed f32x2, exact re-evaluation -- rounds alike and knife-edge decisions (d2 == radius_sqr up to an
+// ulp, e.g. an equal-mass pair at ratio 1) fall the same way as in simple_bh (tests compare visit counts with the CPU walk).
+__device__ __forceinline__ real bh_d2(real dx, real dy, real dz)
+{
+#if NB200_PRECISION == 2
+	return fma(dz, dz, fma(dx, dx, __dmul_rn(dy, dy)));
+#else
+	return fmaf(dz, dz, fmaf(dx, dx, __fmul_rn(dy, dy)));
+#endif
+}
+
 // Accepted node: same force form as the direct kernel, reusing the separation d = me - node and d2 of the
 // acceptance test (clamp applied after the test, as in kfcompute_heap_bh_stackless, impl.cu:399-413).
 // a += m (node - me) / r^3  ==  a -= m d / r^3
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(256) bh_walk_thread(const node4* __restrict__ 
 	{
 		const node4	nd = load_node(xyzr, curr);
 		const real dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
-		const real d2 = dx * dx + dy * dy + dz * dz;	// same expression as bh_walk_warp (see the note there)
+		const real d2 = bh_d2(dx, dy, dz);
 		++visits;
 		if(d2 > nd.w)
 		{
@@ -491,10 +504,7 @@ __global__ void __launch_bounds__(256, NB200_BH_WALK_MINB) bh_walk_warp(const no
 		const int	child = curr << 1;
 		awake = awake || (curr == resume);
 		const real	dx = me.x - nd.x, dy = me.y - nd.y, dz = me.z - nd.z;
-		// left to the compiler's contraction on purpose: this form rounds like the reference's (v1 - cm).norm() built
-		// with gcc -O3, so knife-edge decisions (d2 == radius_sqr up to an ulp, e.g. an equal-mass pair at ratio 1)
-		// fall the same way as in simple_bh (tests compare visit counts with the CPU walk)
-		const real	d2 = dx * dx + dy * dy + dz * dz;
+		const real	d2 = bh_d2(dx, dy, dz);
 		const bool	accept = awake && (d2 > nd.w);
 		const bool	open = awake && !accept;
 		if(STATS) { visits += awake ? 1u : 0u; }
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(128, MINB) bh_walk_warp_multi(const node4* __r
 		{
 			awake[k] = awake[k] || (curr == resume[k]);
 			dx[k] = px[k] - nd.x; dy[k] = py[k] - nd.y; dz[k] = pz[k] - nd.z;
-			d2[k] = dx[k] * dx[k] + dy[k] * dy[k] + dz[k] * dz[k];	// same expression as bh_walk_warp (see the note there)
+			d2[k] = bh_d2(dx[k], dy[k], dz[k]);
 			accept[k] = awake[k] && (d2[k] > nd.w);
 			any_accept = any_accept || accept[k];
 			any_open = any_open || (awake[k] && !accept[k]);
@@ -637,6 +647,8 @@ __global__ void __launch_bounds__(128, MINB) bh_walk_warp_multi(const node4* __r
 		atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
 	}
 }
+
+#include "nb200_bh_group.cuh"
 
 // ---- host orchestration ----------------------------------------------------------------------------------------------
 #define BH_CU(call)                                                                                    \
@@ -848,6 +860,34 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	if(ctx->opt_walk_mode == 1)
 	{
 		bh_walk_thread<<<grid, block, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats);
+	}
+	else if(ctx->opt_walk_mode == 0 || ctx->opt_walk_mode == 8)
+	{
+		// grouped walk (nb200_bh_group.cuh), the default: a warp per 32 consecutive leaves, 4 warps per CTA (a deal chunk is a
+		// multiple of 128 leaves or the whole shard, so a group's leaves stay consecutive)
+		const unsigned	ggrid = static_cast<unsigned>((n_targets + 32 * NB200_BHG_WARPS - 1) / (32 * NB200_BHG_WARPS));
+		// longest-walk-first CTA order from the previous walk's costs: automatic while a GPU has few waves of CTAs
+		// (<= 8192 CTAs = 1M targets per GPU, e.g. 4M bodies over 4 or 8 GPUs); with many waves the tail is a small share
+		// and launching kd-order neighbours together keeps shared upper-tree nodes in L1/L2
+		const bool		lpt = ctx->opt_walk_lpt > 0 || (ctx->opt_walk_lpt < 0 && ggrid >= 1024 && ggrid <= 8192);
+		const int*		order = nullptr;
+		unsigned*		cost = nullptr;
+		if(lpt)
+		{
+			rc = bh_lpt_alloc(l, s, static_cast<int>(ggrid), launches, err);
+			if(rc != NB200_OK) { return rc; }
+			order = s->lpt_have_order ? s->lpt_order : nullptr;
+			cost = s->lpt_cost;
+		}
+		if(stats != nullptr) { bh_walk_group<true><<<ggrid, 32 * NB200_BHG_WARPS, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats, order, cost); }
+		else { bh_walk_group<false><<<ggrid, 32 * NB200_BHG_WARPS, 0, l.stream>>>(s->xyzr, s->nmass, s->body_n, acc_leaf, deal, y, f, n, n_targets, ctx->n_shard, shard_first, stats, order, cost); }
+		if(lpt)
+		{
+			size_t bytes = s->lpt_tmp_bytes;
+			BH_CU(cub::DeviceRadixSort::SortPairsDescending(s->lpt_tmp, bytes, s->lpt_cost, s->lpt_cost_sorted, s->lpt_iota, s->lpt_order,
+															static_cast<int>(ggrid), 0, 32, l.stream));
+			s->lpt_have_order = true;
+		}
 	}
 	else if(ctx->opt_walk_mode != 32)
 	{

@@ -98,7 +98,7 @@ struct nb200_ctx
 	// tunables (0 = automatic)
 	long long	opt_direct_ipt = 0;
 	long long	opt_direct_segments = 0;
-	long long	opt_walk_mode = 0;	// 0 = automatic (two targets per lane), 1 = one thread per target, 2 / 4 = targets per lane, 32 = one target per lane
+	long long	opt_walk_mode = 0;	// 0 = automatic (grouped walk), 8 = grouped walk, 1 = one thread per target, 2 / 4 = targets per lane, 32 = one target per lane
 	long long	opt_walk_threads = 0;
 	long long	opt_walk_lpt = -1;	// longest-walk-first CTA order: -1 automatic (>= 1024 CTAs), 0 off, 1 on
 	long long	opt_timing = 1;

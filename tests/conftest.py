@@ -24,12 +24,15 @@ def load_golden_npz(tag, precision="f64"):
     return dict(np.load(golden_path("%s_%s.npz" % (tag, precision))))
 
 
-def rel_err_per_body(a, b, n):
-    """max_i |a_i - b_i| / |b_i| over bodies, for the acceleration rows of two f vectors (6N) or 3xN blocks."""
+def rel_err_per_body(a, b, n, floor=0.0):
+    """max_i |a_i - b_i| / |b_i| over bodies, for the acceleration rows of two f vectors (6N) or 3xN blocks.
+    floor > 0: |b_i| is taken as at least floor * max_j |b_j| (bodies whose attractions cancel by symmetry)."""
     a = np.asarray(a, dtype=np.float64).reshape(-1, n)[-3:]
     b = np.asarray(b, dtype=np.float64).reshape(-1, n)[-3:]
     num = np.sqrt(((a - b) ** 2).sum(axis=0))
     den = np.sqrt((b ** 2).sum(axis=0))
+    if floor > 0:
+        den = np.maximum(den, floor * den.max())
     return float((num / den).max())
 
 

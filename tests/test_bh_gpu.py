@@ -63,12 +63,17 @@ def test_bh_huge_ratio_equals_direct():
 
 
 def test_bh_walk_modes_bit_identical():
+    """The walks that keep one traversal state per target (thread per target, one / two / four targets per lane) add a
+    target's accepted nodes in the order of nbody_space_heap_stackless::traverse: bit-identical to each other."""
     g = load_golden_npz("g1_n2048")
-    (a,), _, sa = run_bh(g["y"], g["mass"], 10.0, walk_mode=0, stats=True)
+    (a,), _, sa = run_bh(g["y"], g["mass"], 10.0, walk_mode=2, stats=True)
     for mode in (1, 32):
         (b,), _, sb = run_bh(g["y"], g["mass"], 10.0, walk_mode=mode, stats=True)
         assert np.array_equal(a, b)
         assert sa == sb and sa[0] > sa[1] > 0
+
+
+GROUP_TOL = {"f64": 1e-13, "f32": 3e-4}
 
 
 @pytest.mark.parametrize("precision", ["f64", "f32"])
@@ -77,7 +82,8 @@ def test_bh_walk_modes_bit_identical():
 def test_bh_several_targets_per_lane_bit_identical(precision, n, ratio, devices):
     """walk_mode 2 / 4: one warp walks the union of 64 / 128 consecutive leaves (2 / 4 targets per lane); every target
     still accepts exactly the nodes of its own stackless traversal, so forces and visit counts equal walk_mode 32 (one
-    target per lane). walk_mode 0, the default, is two targets per lane."""
+    target per lane). walk_mode 0 / 8, the default, is the grouped walk (nb200_bh_group.cuh): the same accepted nodes per
+    target (equal visit and interaction counts), added in another order -- equal to rounding, not bit for bit."""
     y, m = universe(n, precision) if n >= 128 else (None, None)   # make_universe rounds up to 2 x 64 bodies
     if y is None:
         g = load_golden_npz("g1_n128", precision)
@@ -85,10 +91,45 @@ def test_bh_several_targets_per_lane_bit_identical(precision, n, ratio, devices)
         y = np.concatenate([g["y"][r * 128 + idx] for r in range(6)])
         m = g["mass"][idx]
     (a,), _, sa = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=32, stats=True)
-    for mode in (0, 2, 4):
+    for mode in (2, 4):
         (b,), _, sb = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=mode, stats=True)
         assert np.array_equal(a, b), "walk_mode %d" % mode
         assert sa == sb
+    for mode in (0, 8):
+        (b,), _, sb = run_bh(y, m, ratio, precision=precision, devices=devices, walk_mode=mode, stats=True)
+        assert sa == sb, "walk_mode %d: visits / interactions %r != %r" % (mode, sb, sa)
+        assert np.array_equal(a[:3 * n], b[:3 * n])
+        assert rel_err_per_body(b, a, n) <= GROUP_TOL[precision], "walk_mode %d" % mode
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_bh_grouped_walk_deterministic_and_shard_independent(precision):
+    """The grouped walk's summation order is a pure function of the inputs: two runs agree bit for bit, and so do runs
+    with 1, 2 and 4 shards (a group is the same 32 consecutive leaves however the chunks are dealt)."""
+    y, m = universe(65536, precision)
+    (a,), _, _ = run_bh(y, m, 10.0, precision=precision)
+    (b,), _, _ = run_bh(y, m, 10.0, precision=precision)
+    assert np.array_equal(a, b)
+    for devices in ("0,0", "0,0,0,0"):
+        (c,), _, _ = run_bh(y, m, 10.0, precision=precision, devices=devices)
+        assert np.array_equal(a, c), devices
+
+
+def test_bh_grouped_walk_knife_edge_counts(oracle64):
+    """Certified FP32 decisions: bodies on a lattice with equal masses put many (target, node) pairs exactly on
+    d2 == radius_sqr; every such test must fall back to the FP64 expression and decide as simple_bh does."""
+    k = 16
+    g = np.arange(k, dtype=np.float64)
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)      # 4096 lattice points, spacing 1
+    n = pos.shape[0]
+    y = np.concatenate([pos[:, 0], pos[:, 1], pos[:, 2], np.zeros(3 * n)])
+    m = np.ones(n)
+    for ratio in (1.0, 2.0, 10.0):
+        t = oracle64.heap_build(y, m, ratio)
+        want, visits, inter = oracle64.fcompute_bh(y, m, t)
+        (f,), _, st = run_bh(y, m, ratio, stats=True)
+        assert st == (visits, inter), ratio
+        assert rel_err_per_body(f, want, n, floor=1e-9) <= 1e-12, ratio
 
 
 @pytest.mark.parametrize("devices", ["0", "0,0"])
