@@ -84,21 +84,54 @@ struct alignas(16) bhg_warp_smem
 #endif
 };
 
+// One accepted node for one target: the arithmetic of node_force_from_test, term by term. A lane the node is not for
+// (`mine` == 0) adds it with zero mass, i.e. exactly +-0: no branch, so the dependent chains of several entries
+// interleave (ptxas turns predicated DFMAs into three 64-bit selects; selecting the mass costs one).
+// CLAMP = false leaves out the max(r^2, MinDistance) of nbody_data::force (nbody_data.cpp:39-42): only for rounds in
+// which no accepted pair can be closer than 1e-4.
+template<bool CLAMP>
+__device__ __forceinline__ void bhg_force(real dx, real dy, real dz, real m, unsigned mine, real& ax, real& ay, real& az)
+{
+	real d2 = bh_d2(dx, dy, dz);
+	m = mine != 0 ? m : static_cast<real>(0);
+#if NB200_PRECISION == 2
+	if(CLAMP)
+	{
+		long long		bits = __double_as_longlong(d2);
+		const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8
+		bits = bits < min_bits ? min_bits : bits;
+		d2 = __longlong_as_double(bits);
+	}
+	double	y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
+	const double h = d2 * y0;
+	const double e = fma(-h, y0, 1.0);
+	const double p = fma(e, 0.375, 0.5);
+	const double q = y0 * e;
+	const double yv = fma(q, p, y0);
+	const double c = (yv * yv) * (m * yv);
+#else
+	if(CLAMP) { d2 = fmaxf(d2, NB200_MIN_DISTANCE); }
+	const float yv = rsqrtf(d2);
+	const float c = (yv * yv) * (m * yv);
+#endif
+	ax = fma(-dx, c, ax);
+	ay = fma(-dy, c, ay);
+	az = fma(-dz, c, az);
+}
+
 // sum phase: one target per lane runs down the warp's interaction list. The list holds the nodes themselves (written by
 // the lane that tested them), so this loop touches shared memory only: every read is one broadcast.
-__device__ __forceinline__ void bhg_flush(const bhg_warp_smem& sm, int count, int lane, real px, real py, real pz,
+template<bool CLAMP>
+__device__ __forceinline__ void bhg_flush(const bhg_warp_smem& sm, int count, unsigned lane_bit, real px, real py, real pz,
 										  real& ax, real& ay, real& az)
 {
-	// No branch on the mask: a lane the node is not for adds it with zero mass (exactly +-0), which lets the compiler
-	// interleave the dependent FP64 chains of four entries.
 #pragma unroll 4
 	for(int e = 0; e < count; ++e)
 	{
 		const unsigned	mask = sm.lmask[e];
 		const body4		nd = sm.lnode[e];
-		const real		m = ((mask >> lane) & 1u) ? nd.m : static_cast<real>(0);
-		const real		dx = px - nd.x, dy = py - nd.y, dz = pz - nd.z;
-		node_force_from_test(dx, dy, dz, bh_d2(dx, dy, dz), m, ax, ay, az);
+		bhg_force<CLAMP>(px - nd.x, py - nd.y, pz - nd.z, nd.m, mask & lane_bit, ax, ay, az);
 	}
 }
 
@@ -148,6 +181,9 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 		for(int o = 16; o > 0; o >>= 1) { rad = fmaxf(rad, __shfl_xor_sync(full, rad, o)); }
 		const float		MU = 1.9073486328125e-6f;	// 32 * 2^-24
 		const float		MUR2 = MU * (rad * rad) * 1.001f;
+		// a pair closer than MinDistance (d2 < 1e-8) on a node with radius_sqr < 1e-8 has t = d2 - radius_sqr < 1e-8 and an
+		// FP32 error below u (7 R d + 10 d^2 + 4 w) < 5e-11 R: every such test shows |t| < CLOSE
+		const float		CLOSE = 2.0e-8f + 1.0e-10f * rad;
 		sm.tpd[0][lane] = me.x;
 		sm.tpd[1][lane] = me.y;
 		sm.tpd[2][lane] = me.z;
@@ -161,7 +197,13 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			reinterpret_cast<float*>(&sm.tp_z[lane >> 1])[lane & 1] = fz;
 		}
 		const unsigned	live_mask = __ballot_sync(full, live);
+		const unsigned	lane_bit = 1u << lane;
 		int				sp = 0, nl = 0;	// warp-uniform fill of the stack and of the list
+		// warp-uniform: the list may hold an accepted (target, node) pair closer than MinDistance, so the next sum needs the
+		// clamp of r^2. d2 > radius_sqr >= 0 for every accepted pair, so that takes a node with radius_sqr < 1e-8 (a leaf)
+		// AND a target within 1e-4 of it: known from the smallest |d2 - radius_sqr| the lane saw (FP64 build; the group's
+		// own leaves raise it, a few % of the rounds). The FP32 build's clamp is one FMNMX and stays on.
+		bool			close_pairs = true;	// the root's entry is not examined
 		{
 			// the root is visited by every target (curr = 1 at the start of traverse)
 			const node4	nd = load_node(xyzr, 1);
@@ -205,7 +247,8 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			real			massL, massR;
 			bhg_load_mass_pair(nmass, L, massL, massR);
 			// ---- sum: while those loads are in flight, every target adds the nodes accepted in the previous round ----
-			bhg_flush(sm, nl, lane, me.x, me.y, me.z, ax, ay, az);
+			if(close_pairs) { bhg_flush<true>(sm, nl, lane_bit, me.x, me.y, me.z, ax, ay, az); }
+			else { bhg_flush<false>(sm, nl, lane_bit, me.x, me.y, me.z, ax, ay, az); }
 			nl = 0;
 			__syncwarp();
 			unsigned		SL = 0, SR = 0;	// bit j = 1: target j does NOT accept the child
@@ -283,7 +326,10 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 #endif
 			const unsigned	AL = ~SL & M, AR = ~SR & M;	// accepted by
 			const unsigned	OL = SL & M, OR_ = SR & M;	// opened by
-			const unsigned	lt = (1u << lane) - 1u;
+			const unsigned	lt = lane_bit - 1u;
+#if NB200_PRECISION == 2
+			close_pairs = __any_sync(full, (AL != 0 && uL < CLOSE) || (AR != 0 && uR < CLOSE));
+#endif
 			{
 				// accepted nodes -> interaction list (left children first, lanes in order)
 				const unsigned bL = __ballot_sync(full, AL != 0), bR = __ballot_sync(full, AR != 0);
@@ -323,7 +369,8 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			}
 			__syncwarp();
 		}
-		bhg_flush(sm, nl, lane, me.x, me.y, me.z, ax, ay, az);
+		if(close_pairs) { bhg_flush<true>(sm, nl, lane_bit, me.x, me.y, me.z, ax, ay, az); }
+		else { bhg_flush<false>(sm, nl, lane_bit, me.x, me.y, me.z, ax, ay, az); }
 		if(live)
 		{
 			if(acc_leaf != nullptr)
