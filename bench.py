@@ -373,6 +373,7 @@ def measure(args, kind, n, steps, warmup, ctxinfo, want_clocks):
         eng.synchronize()
         v, k = eng.bh_walk_stats(False)
         out["walk_counts"] = (dist.sum_over_ranks(v), dist.sum_over_ranks(k))
+        out["walk_profile"] = eng.bh_walk_profile()     # this rank's walk (rank 0 is reported)
     # ---- FP64 / FP32 FMA peak probe (same process, same clocks) ----
     out["fma_peak"] = eng.probe_fma_peak(300.0) if rank == 0 else 0.0
     out["eng"] = eng
@@ -446,7 +447,7 @@ def bh_roofline(args, r, world):
     return {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
             "kernel": "Barnes-Hut walk (all walk launches of one fcompute)", "kernel_ms": force_ms, "phases_ms": r["phases"],
-            "node_visits": visits, "interactions": inter,
+            "node_visits": visits, "interactions": inter, "walk_profile_rank0": r.get("walk_profile"),
             "algorithmic_per_unit": "%d FMA-pipe slots = %d flop per accepted (target, node) interaction; node visits are "
                                     "decided on the other pipe and are not counted" % (slots, 2 * slots),
             "peak_source": "nb200_probe_fma_peak (this run)",

@@ -151,6 +151,12 @@ int nb200_bh_export_tree(nb200_ctx* ctx, int lane, nb200_real* xyzr, nb200_real*
  * context's targets (only counted when enabled; costs two atomics per target). */
 int nb200_bh_walk_stats(nb200_ctx* ctx, int enable, unsigned long long* visits,
 						unsigned long long* interactions);
+/* Profile of the last counted grouped walk (counting on, see nb200_bh_walk_stats; summed over lanes): out[0] rounds
+ * (one work item per lane each), [1] work items (sibling pairs tested against a group of 32 targets), [2] interaction-list
+ * entries (accepted node + target mask), [3] lane-items whose FP32 decisions were redone in FP64, [4] rounds summed with
+ * the MinDistance clamp, [5] deepest fill of a warp's item stack, [6] sum over rounds of the busiest target's entries,
+ * [7] sum over groups of the busiest target's entries over the whole walk. Instrumentation only. */
+int nb200_bh_walk_profile(nb200_ctx* ctx, unsigned long long out[8]);
 
 /* ---- state-vector ops ------------------------------------------------------
  * (nbody_engine_cuda.cpp:376-530, nbody_engine.cpp:47-113) */

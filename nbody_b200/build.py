@@ -27,8 +27,11 @@ NVCC_FLAGS = [
 PRECISIONS = {"f64": 2, "f32": 1}
 
 
-def lib_path(precision):
-    return os.path.join(CSRC, "libnb200_%s.so" % precision)
+def lib_path(precision, variant=None):
+    """The product library; `variant` (or the environment variable NB200_LIB_VARIANT) names an A/B build made with
+    build_variant() -- measurement only, never shipped."""
+    variant = variant if variant is not None else os.environ.get("NB200_LIB_VARIANT", "")
+    return os.path.join(CSRC, "libnb200_%s%s.so" % (precision, "_" + variant if variant else ""))
 
 
 def adapter_path(precision):
@@ -51,7 +54,7 @@ def _sources(folder, exts):
 
 
 def build_kernels(precision, force=False, verbose=False):
-    out = lib_path(precision)
+    out = lib_path(precision, "")
     deps = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "nb200.h")]
     if not force and _newer(out, deps):
         return out
@@ -60,6 +63,15 @@ def build_kernels(precision, force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def build_variant(precision, variant, defines):
+    """A/B build of the kernel library with extra -D flags, e.g. build_variant("f64", "minb6", ["NB200_BHG_MINB=6"])."""
+    out = lib_path(precision, variant)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DNB200_PRECISION=%d" % PRECISIONS[precision]] + ["-D" + d for d in defines] + [
+        "-o", out, os.path.join(CSRC, "nb200_api.cu"), "-ldl"]
     subprocess.run(cmd, check=True)
     return out
 

@@ -326,8 +326,8 @@ NB200_API int nb200_create(nb200_ctx** out, const int* dev_ids, int nlanes, int 
 				  cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess &&
 				  cudaEventCreateWithFlags(&l.ev_packed, cudaEventDisableTiming) == cudaSuccess &&
 				  cudaEventCreateWithFlags(&l.ev_gathered, cudaEventDisableTiming) == cudaSuccess &&
-				  cudaMalloc(&l.d_scalar, 8 * sizeof(unsigned long long)) == cudaSuccess &&
-				  cudaMallocHost(&l.h_scalar, 8 * sizeof(unsigned long long)) == cudaSuccess;
+				  cudaMalloc(&l.d_scalar, 32 * sizeof(unsigned long long)) == cudaSuccess &&
+				  cudaMallocHost(&l.h_scalar, 32 * sizeof(unsigned long long)) == cudaSuccess;
 		for(int e = 0; e < 5 && ok; ++e) { ok = cudaEventCreate(&l.ev_t[e]) == cudaSuccess; }
 		for(int e = 0; e < 8 && ok; ++e) { ok = cudaEventCreate(&l.ev_mark[e]) == cudaSuccess; }
 		if(!ok)
@@ -1251,6 +1251,24 @@ NB200_API int nb200_bh_walk_stats(nb200_ctx* ctx, int enable, unsigned long long
 	if(visits) { *visits = v; }
 	if(interactions) { *interactions = k; }
 	ctx->bh_stats = enable != 0;
+	return NB200_OK;
+}
+
+NB200_API int nb200_bh_walk_profile(nb200_ctx* ctx, unsigned long long out[8])
+{
+	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
+	step_invalidate(ctx);
+	for(int q = 0; q < 8; ++q) { out[q] = 0; }
+	for(auto& l : ctx->lanes)
+	{
+		CU(ctx, cudaSetDevice(l.dev));
+		CU(ctx, cudaMemcpyAsync(l.h_scalar + 8, l.d_scalar + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+		CU(ctx, cudaStreamSynchronize(l.stream));
+		for(int q = 0; q < 8; ++q)
+		{
+			out[q] = q == 5 ? std::max(out[q], l.h_scalar[8 + q]) : out[q] + l.h_scalar[8 + q];
+		}
+	}
 	return NB200_OK;
 }
 

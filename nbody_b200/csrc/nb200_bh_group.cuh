@@ -35,11 +35,16 @@
 #define NB200_BH_GROUP_CUH
 
 #define NB200_BHG_WARPS 4			// groups (warps) per CTA
-#define NB200_BHG_STACK 768			// work-item slots per warp
-#define NB200_BHG_STACK_SOFT 704	// above this fill items are taken one at a time (depth-first: growth <= tree depth)
+#ifndef NB200_BHG_STACK
+#define NB200_BHG_STACK 512			// work-item slots per warp (deepest fill measured at N = 4M, ratio 10: 372)
+#endif
+#define NB200_BHG_STACK_SOFT (NB200_BHG_STACK - 64)	// above this fill items are taken one at a time (depth-first: growth <= tree depth)
 #define NB200_BHG_LIST 64			// interaction-list entries per warp: one round of 32 sibling pairs
 #ifndef NB200_BHG_MINB
 #define NB200_BHG_MINB 5
+#endif
+#ifndef NB200_BHG_UNROLL
+#define NB200_BHG_UNROLL 4			// entries of the sum loop in flight per lane
 #endif
 
 typedef unsigned long long bhg_f32x2;
@@ -72,7 +77,7 @@ __device__ __forceinline__ bhg_f32x2 bhg_sub(bhg_f32x2 a, bhg_f32x2 b)
 	return d;
 }
 
-struct alignas(16) bhg_warp_smem
+struct bhg_warp_smem
 {
 	int2				stack[NB200_BHG_STACK];	// {parent, mask of targets that opened it}
 	body4				lnode[NB200_BHG_LIST];	// interaction list: accepted node {mass centre, mass} ...
@@ -104,12 +109,22 @@ __device__ __forceinline__ void bhg_force(real dx, real dy, real dz, real m, uns
 	}
 	double	y0;
 	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
+#ifndef NB200_BHG_NEWTON
+	// m r^-3 = m y0^3 (1 + e (3/2 + 15/8 e)) with e = 1 - r^2 y0^2 exact to one rounding (y0 has 21 significant bits, so
+	// y0^2 is exact): 7 FP64 operations instead of 8, truncation error 35/16 e^3 < 2^-58
+	const double y2 = y0 * y0;
+	const double e = fma(-d2, y2, 1.0);
+	const double u = e * fma(e, 1.875, 1.5);
+	const double g = (m * y0) * y2;
+	const double c = fma(g, u, g);
+#else
 	const double h = d2 * y0;
 	const double e = fma(-h, y0, 1.0);
 	const double p = fma(e, 0.375, 0.5);
 	const double q = y0 * e;
 	const double yv = fma(q, p, y0);
 	const double c = (yv * yv) * (m * yv);
+#endif
 #else
 	if(CLAMP) { d2 = fmaxf(d2, NB200_MIN_DISTANCE); }
 	const float yv = rsqrtf(d2);
@@ -126,7 +141,8 @@ template<bool CLAMP>
 __device__ __forceinline__ void bhg_flush(const bhg_warp_smem& sm, int count, unsigned lane_bit, real px, real py, real pz,
 										  real& ax, real& ay, real& az)
 {
-#pragma unroll 4
+	constexpr int in_flight = NB200_BHG_UNROLL;
+#pragma unroll in_flight
 	for(int e = 0; e < count; ++e)
 	{
 		const unsigned	mask = sm.lmask[e];
@@ -172,6 +188,7 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 		const node4	me = load_node(xyzr, leaf);
 		real		ax = 0, ay = 0, az = 0;
 		unsigned	visits = 0, inter = 0;
+		unsigned	pr_rounds = 0, pr_items = 0, pr_entries = 0, pr_unsure = 0, pr_close = 0, pr_maxsp = 0, pr_trips = 0, pr_mine = 0;	// STATS only
 #if NB200_PRECISION == 2
 		// group frame: origin = first target; R = largest |relative coordinate| in the group
 		const double	ox = __shfl_sync(full, me.x, 0), oy = __shfl_sync(full, me.y, 0), oz = __shfl_sync(full, me.z, 0);
@@ -247,6 +264,19 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			real			massL, massR;
 			bhg_load_mass_pair(nmass, L, massL, massR);
 			// ---- sum: while those loads are in flight, every target adds the nodes accepted in the previous round ----
+			if(STATS)
+			{
+				// what a per-lane compaction of this round's entries would cost: the largest number of entries any one target takes
+				unsigned mine = 0;
+				for(int e = 0; e < nl; ++e) { mine += (sm.lmask[e] & lane_bit) ? 1u : 0u; }
+				pr_trips += __reduce_max_sync(full, mine);
+				pr_mine += mine;
+				pr_rounds += 1;
+				pr_items += cnt;
+				pr_entries += nl;
+				pr_close += close_pairs ? 1u : 0u;
+				pr_maxsp = max(pr_maxsp, static_cast<unsigned>(sp + cnt));
+			}
 			if(close_pairs) { bhg_flush<true>(sm, nl, lane_bit, me.x, me.y, me.z, ax, ay, az); }
 			else { bhg_flush<false>(sm, nl, lane_bit, me.x, me.y, me.z, ax, ay, az); }
 			nl = 0;
@@ -281,6 +311,7 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			}
 			// some test of this item fell inside the margin (or is NaN): the lane redoes its 64 tests in FP64, exactly
 			const bool unsure = have && !(uL > mL && uR > mR);
+			if(STATS) { pr_unsure += __popc(__ballot_sync(full, unsure)); }
 			if(__any_sync(full, unsure))
 			{
 				if(unsure)
@@ -388,6 +419,25 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 		{
 			atomicAdd(stats + 2, static_cast<unsigned long long>(visits));
 			atomicAdd(stats + 3, static_cast<unsigned long long>(inter));
+		}
+		if(STATS)
+		{
+			// the busiest target's entries over the whole walk (what a perfectly elastic per-lane compaction would still pay);
+			// the last round's entries are left out of this one counter
+			const unsigned busiest = __reduce_max_sync(full, pr_mine);
+			if(lane == 0) { atomicAdd(stats + 15, static_cast<unsigned long long>(busiest)); }
+		}
+		if(STATS && lane == 0)
+		{
+			// walk profile (nb200_bh_walk_profile): rounds, items, list entries, lane-items redone in FP64, rounds summed
+			// with the clamp, deepest stack fill, sum over rounds of the busiest target's entries
+			atomicAdd(stats + 8, static_cast<unsigned long long>(pr_rounds));
+			atomicAdd(stats + 9, static_cast<unsigned long long>(pr_items));
+			atomicAdd(stats + 10, static_cast<unsigned long long>(pr_entries + nl));
+			atomicAdd(stats + 11, static_cast<unsigned long long>(pr_unsure));
+			atomicAdd(stats + 12, static_cast<unsigned long long>(pr_close));
+			atomicMax(stats + 13, static_cast<unsigned long long>(pr_maxsp));
+			atomicAdd(stats + 14, static_cast<unsigned long long>(pr_trips));
 		}
 	}
 	if(cta_cost != nullptr && threadIdx.x == 0)

@@ -61,7 +61,7 @@ struct nb200_lane
 	real*			sym_acc = nullptr;		// [shard][3][n_shard] reduced accelerations (+ [3][n_shard] receive block)
 	size_t			sym_ntiles = 0;
 	int				sym_edge = 0;
-	unsigned long long*	d_scalar = nullptr;	// device scratch: maxabs bits, walk counters (4 x u64)
+	unsigned long long*	d_scalar = nullptr;	// device scratch (32 x u64): [0] maxabs bits, [2..3] walk counters, [4] probe, [8..15] walk profile
 	unsigned long long*	h_scalar = nullptr;	// pinned mirror
 	bh_state*		bh = nullptr;
 	real*			read_scratch = nullptr;	// [shards][6][n_shard] staging of a multi-rank read_buffer

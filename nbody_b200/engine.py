@@ -74,6 +74,7 @@ def load_library(precision="f64"):
     sig("nb200_fcompute_bh", i32, vp, vp, vp, sz)
     sig("nb200_bh_export_tree", i32, vp, i32, vp, vp, vp)
     sig("nb200_bh_walk_stats", i32, vp, i32, P(ull), P(ull))
+    sig("nb200_bh_walk_profile", i32, vp, P(ull))
     sig("nb200_fmadd_inplace", i32, vp, vp, vp, real)
     sig("nb200_fmadd", i32, vp, vp, vp, vp, real)
     sig("nb200_fmaddn_inplace", i32, vp, vp, P(vp), vp, sz)
@@ -568,6 +569,14 @@ class Engine:
                                                        mass.ctypes.data_as(C.c_void_p), body.ctypes.data_as(C.c_void_p)),
                          "bh_export_tree")
         return (xyzr, mass, body) if rc == 0 else None
+
+    def bh_walk_profile(self):
+        """Counters of the last counted grouped walk (see nb200_bh_walk_profile)."""
+        out = (C.c_ulonglong * 8)()
+        self.lib.nb200_bh_walk_profile(self.ctx, out)
+        keys = ("rounds", "items", "entries", "unsure_lane_items", "clamp_rounds", "max_stack", "busiest_target_entries",
+                "busiest_target_entries_whole_walk")
+        return dict(zip(keys, [int(v) for v in out[:8]]))
 
     def bh_walk_stats(self, enable=True):
         v, k = C.c_ulonglong(0), C.c_ulonglong(0)
