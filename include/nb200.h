@@ -155,8 +155,9 @@ int nb200_bh_walk_stats(nb200_ctx* ctx, int enable, unsigned long long* visits,
  * (one work item per lane each), [1] work items (sibling pairs tested against a group of 32 targets), [2] interaction-list
  * entries (accepted node + target mask), [3] lane-items whose FP32 decisions were redone in FP64, [4] rounds summed with
  * the MinDistance clamp, [5] deepest fill of a warp's item stack, [6] sum over rounds of the busiest target's entries,
- * [7] sum over groups of the busiest target's entries over the whole walk. Instrumentation only. */
-int nb200_bh_walk_profile(nb200_ctx* ctx, unsigned long long out[8]);
+ * [7] sum over groups of the busiest target's entries over the whole walk, [8..12] entries whose mask names 32 / 24..31 /
+ * 16..23 / 8..15 / 1..7 targets (last round of each group left out), [13..15] reserved. Instrumentation only. */
+int nb200_bh_walk_profile(nb200_ctx* ctx, unsigned long long out[16]);
 
 /* ---- state-vector ops ------------------------------------------------------
  * (nbody_engine_cuda.cpp:376-530, nbody_engine.cpp:47-113) */

@@ -1254,17 +1254,17 @@ NB200_API int nb200_bh_walk_stats(nb200_ctx* ctx, int enable, unsigned long long
 	return NB200_OK;
 }
 
-NB200_API int nb200_bh_walk_profile(nb200_ctx* ctx, unsigned long long out[8])
+NB200_API int nb200_bh_walk_profile(nb200_ctx* ctx, unsigned long long out[16])
 {
 	if(ctx == nullptr || out == nullptr) { return NB200_ERR_ARG; }
 	step_invalidate(ctx);
-	for(int q = 0; q < 8; ++q) { out[q] = 0; }
+	for(int q = 0; q < 16; ++q) { out[q] = 0; }
 	for(auto& l : ctx->lanes)
 	{
 		CU(ctx, cudaSetDevice(l.dev));
-		CU(ctx, cudaMemcpyAsync(l.h_scalar + 8, l.d_scalar + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+		CU(ctx, cudaMemcpyAsync(l.h_scalar + 8, l.d_scalar + 8, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
 		CU(ctx, cudaStreamSynchronize(l.stream));
-		for(int q = 0; q < 8; ++q)
+		for(int q = 0; q < 16; ++q)
 		{
 			out[q] = q == 5 ? std::max(out[q], l.h_scalar[8 + q]) : out[q] + l.h_scalar[8 + q];
 		}

@@ -846,7 +846,7 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	if(ctx->bh_stats)
 	{
 		BH_CU(cudaMemsetAsync(l.d_scalar + 2, 0, 2 * sizeof(unsigned long long), l.stream));
-		BH_CU(cudaMemsetAsync(l.d_scalar + 8, 0, 8 * sizeof(unsigned long long), l.stream));
+		BH_CU(cudaMemsetAsync(l.d_scalar + 8, 0, 16 * sizeof(unsigned long long), l.stream));
 		stats = l.d_scalar;
 	}
 	const int	n_targets = static_cast<int>(ctx->n_shard);

@@ -44,7 +44,7 @@
 #define NB200_BHG_MINB 5
 #endif
 #ifndef NB200_BHG_UNROLL
-#define NB200_BHG_UNROLL 4			// entries of the sum loop in flight per lane
+#define NB200_BHG_UNROLL 8			// entries of the sum loop in flight per lane
 #endif
 
 typedef unsigned long long bhg_f32x2;
@@ -89,16 +89,20 @@ struct bhg_warp_smem
 #endif
 };
 
-// One accepted node for one target: the arithmetic of node_force_from_test, term by term. A lane the node is not for
-// (`mine` == 0) adds it with zero mass, i.e. exactly +-0: no branch, so the dependent chains of several entries
-// interleave (ptxas turns predicated DFMAs into three 64-bit selects; selecting the mass costs one).
+// One accepted node for one target. Same formulas as node_force_from_test, with m r^-3 taken from the seed in one series
+// step (FP64 build): m y0^3 (1 + e (3/2 + 15/8 e)), e = 1 - r^2 y0^2 exact to one rounding (the seed has 21 significant
+// bits, so y0^2 is exact) -- 7 FP64 operations instead of 8, truncation error 35/16 e^3 < 2^-56. On this pipe an FP64
+// instruction holds the dispatch port for two cycles and everything else for one (profiles/microbench/bh_sum_loop.cu),
+// so what counts is 2 x FP64 + other instructions per entry.
+// A lane the node is not for (`mine` == 0) adds it with a zero coefficient, i.e. exactly +-0: no branch, so the
+// dependent chains of several entries interleave; the zero enters through the seed, whose low word is zero anyway
+// (one select; ptxas turns predicated DFMAs into three 64-bit selects).
 // CLAMP = false leaves out the max(r^2, MinDistance) of nbody_data::force (nbody_data.cpp:39-42): only for rounds in
 // which no accepted pair can be closer than 1e-4.
 template<bool CLAMP>
 __device__ __forceinline__ void bhg_force(real dx, real dy, real dz, real m, unsigned mine, real& ax, real& ay, real& az)
 {
 	real d2 = bh_d2(dx, dy, dz);
-	m = mine != 0 ? m : static_cast<real>(0);
 #if NB200_PRECISION == 2
 	if(CLAMP)
 	{
@@ -107,27 +111,17 @@ __device__ __forceinline__ void bhg_force(real dx, real dy, real dz, real m, uns
 		bits = bits < min_bits ? min_bits : bits;
 		d2 = __longlong_as_double(bits);
 	}
-	double	y0;
-	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
-#ifndef NB200_BHG_NEWTON
-	// m r^-3 = m y0^3 (1 + e (3/2 + 15/8 e)) with e = 1 - r^2 y0^2 exact to one rounding (y0 has 21 significant bits, so
-	// y0^2 is exact): 7 FP64 operations instead of 8, truncation error 35/16 e^3 < 2^-58
+	double	seed;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(d2));
+	const double y0 = __hiloint2double(mine != 0 ? __double2hiint(seed) : 0, 0);
 	const double y2 = y0 * y0;
 	const double e = fma(-d2, y2, 1.0);
 	const double u = e * fma(e, 1.875, 1.5);
 	const double g = (m * y0) * y2;
 	const double c = fma(g, u, g);
 #else
-	const double h = d2 * y0;
-	const double e = fma(-h, y0, 1.0);
-	const double p = fma(e, 0.375, 0.5);
-	const double q = y0 * e;
-	const double yv = fma(q, p, y0);
-	const double c = (yv * yv) * (m * yv);
-#endif
-#else
 	if(CLAMP) { d2 = fmaxf(d2, NB200_MIN_DISTANCE); }
-	const float yv = rsqrtf(d2);
+	const float yv = mine != 0 ? rsqrtf(d2) : 0.0f;
 	const float c = (yv * yv) * (m * yv);
 #endif
 	ax = fma(-dx, c, ax);
@@ -189,6 +183,7 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 		real		ax = 0, ay = 0, az = 0;
 		unsigned	visits = 0, inter = 0;
 		unsigned	pr_rounds = 0, pr_items = 0, pr_entries = 0, pr_unsure = 0, pr_close = 0, pr_maxsp = 0, pr_trips = 0, pr_mine = 0;	// STATS only
+		unsigned	pr_hist[5] = {0, 0, 0, 0, 0};	// entries by targets per mask: 32, 24..31, 16..23, 8..15, 1..7
 #if NB200_PRECISION == 2
 		// group frame: origin = first target; R = largest |relative coordinate| in the group
 		const double	ox = __shfl_sync(full, me.x, 0), oy = __shfl_sync(full, me.y, 0), oz = __shfl_sync(full, me.z, 0);
@@ -268,7 +263,13 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			{
 				// what a per-lane compaction of this round's entries would cost: the largest number of entries any one target takes
 				unsigned mine = 0;
-				for(int e = 0; e < nl; ++e) { mine += (sm.lmask[e] & lane_bit) ? 1u : 0u; }
+				for(int e = 0; e < nl; ++e)
+				{
+					const unsigned mk = sm.lmask[e];
+					mine += (mk & lane_bit) ? 1u : 0u;
+					const int pc = __popc(mk);
+					pr_hist[pc == 32 ? 0 : (pc >= 24 ? 1 : (pc >= 16 ? 2 : (pc >= 8 ? 3 : 4)))] += 1;
+				}
 				pr_trips += __reduce_max_sync(full, mine);
 				pr_mine += mine;
 				pr_rounds += 1;
@@ -438,6 +439,7 @@ bh_walk_group(const node4* __restrict__ xyzr, const real* __restrict__ nmass, co
 			atomicAdd(stats + 12, static_cast<unsigned long long>(pr_close));
 			atomicMax(stats + 13, static_cast<unsigned long long>(pr_maxsp));
 			atomicAdd(stats + 14, static_cast<unsigned long long>(pr_trips));
+			for(int q = 0; q < 5; ++q) { atomicAdd(stats + 16 + q, static_cast<unsigned long long>(pr_hist[q])); }
 		}
 	}
 	if(cta_cost != nullptr && threadIdx.x == 0)

@@ -572,11 +572,11 @@ class Engine:
 
     def bh_walk_profile(self):
         """Counters of the last counted grouped walk (see nb200_bh_walk_profile)."""
-        out = (C.c_ulonglong * 8)()
+        out = (C.c_ulonglong * 16)()
         self.lib.nb200_bh_walk_profile(self.ctx, out)
         keys = ("rounds", "items", "entries", "unsure_lane_items", "clamp_rounds", "max_stack", "busiest_target_entries",
-                "busiest_target_entries_whole_walk")
-        return dict(zip(keys, [int(v) for v in out[:8]]))
+                "busiest_target_entries_whole_walk", "entries_32", "entries_24_31", "entries_16_23", "entries_8_15", "entries_1_7")
+        return dict(zip(keys, [int(v) for v in out[:13]]))
 
     def bh_walk_stats(self, enable=True):
         v, k = C.c_ulonglong(0), C.c_ulonglong(0)
