@@ -41,6 +41,13 @@ def main():
         f = e.create_buffer(e.get_y().size())
         e.fcompute(0.0, e.get_y(), f)
         got = e.read_buffer(f)                      # collective: every rank receives the full vector
+        # shard-local read: only this rank's columns land in the full-layout host array, nothing else is touched
+        loc = np.full(got.shape, np.nan)
+        e.read_local_into(loc.ctypes.data, f)
+        lo, hi = dist.shard_range(n, world, rank)
+        mine = np.zeros((6, n), dtype=bool)
+        mine[:, lo:hi] = True
+        assert np.array_equal(loc.reshape(6, n)[mine], got.reshape(6, n)[mine]) and np.isnan(loc.reshape(6, n)[~mine]).all()
         tmp = e.create_buffer(e.get_y().size())
         e.fmaddn(tmp, e.get_y(), [f], np.array([1e-3]))
         stage = e.read_buffer(tmp)
