@@ -228,9 +228,13 @@ int nb200_elapsed_ms(nb200_ctx* ctx, int slot_a, int slot_b, float* ms);
  * ~`ms` milliseconds and returns achieved FMA instructions (per lane) per second. */
 int nb200_probe_fma_peak(nb200_ctx* ctx, double ms, double* fma_lane_per_s);
 /* Tunables: "direct_targets_per_thread" (1, 2, 4), "direct_segments", "direct_symmetric" / "direct_small" (-1 automatic,
- * 0 off, 1 on), "direct_sym_tile" (power of two, 256..8192), "walk_mode" (0 = automatic: warp-coherent walk
- * with two targets per lane; 1 = one thread per target; 2 / 4 = targets per lane; 32 = one target per lane), "walk_lpt" (walk CTAs launched longest
- * walk first: -1 automatic, 0 off, 1 on), "timing" (0/1: phase events), "step_graph" (0/1, above). 0 = automatic where applicable. */
+ * 0 off, 1 on), "direct_sym_tile" (power of two, 256..8192), "walk_mode" (0 = automatic = 8: grouped
+ * walk, lanes on nodes while deciding and on targets while summing; 1 = one thread per target; 32 / 2 / 4 = warp-coherent walk
+ * with one / two / four targets per lane), "walk_lpt" (walk CTAs launched longest walk first: -1 automatic, 0 off, 1 on),
+ * "timing" (0/1: phase events), "step_graph" (0/1, above), "use_nccl" (0/1: the lanes of ONE process exchange shards with
+ * NCCL, one communicator per lane from ncclCommInitAll -- the reference's use_nccl=1, nbody_engine_cuda.cpp:100-106 --
+ * instead of peer copies and peer loads; needs distinct devices, NB200_ERR_UNSUPPORTED otherwise and nothing changes).
+ * 0 = automatic where applicable. */
 int nb200_set_option(nb200_ctx* ctx, const char* name, long long value);
 
 #ifdef __cplusplus

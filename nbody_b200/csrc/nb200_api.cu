@@ -143,6 +143,24 @@ int gather_blocks(nb200_ctx* ctx, int which)
 									 NB200_NCCL_REAL, static_cast<ncclComm_t>(ctx->comm), l.stream));
 		return NB200_OK;
 	}
+	if(ctx->lanes.size() > 1 && ctx->lanes_nccl)
+	{
+		// one process, one communicator per lane (ncclCommInitAll): the reference's use_nccl=1 (nbody_engine_cuda.cpp:626-751)
+		NC(ctx, ctx->nccl->GroupStart());
+		for(auto& l : ctx->lanes)
+		{
+			char* base = gather_base(l, which);
+			ncclResult_t r = ctx->nccl->AllGather(base + static_cast<size_t>(l.shard) * shard_bytes, base, ctx->n_shard * reals_per_body,
+												  NB200_NCCL_REAL, static_cast<ncclComm_t>(l.lane_comm), l.stream);
+			if(r != ncclSuccess)
+			{
+				ctx->nccl->GroupEnd();
+				return fail(ctx, NB200_ERR_NCCL, "ncclAllGather (lane %d): %s", l.shard, ctx->nccl->GetErrorString(r));
+			}
+		}
+		NC(ctx, ctx->nccl->GroupEnd());
+		return NB200_OK;
+	}
 	if(ctx->lanes.size() > 1)
 	{
 		for(auto& l : ctx->lanes)
@@ -418,6 +436,11 @@ NB200_API int nb200_destroy(nb200_ctx* ctx)
 	{
 		ctx->nccl->CommDestroy(static_cast<ncclComm_t>(ctx->comm));
 	}
+	for(auto& l : ctx->lanes)
+	{
+		if(l.lane_comm != nullptr && ctx->nccl != nullptr) { ctx->nccl->CommDestroy(static_cast<ncclComm_t>(l.lane_comm)); }
+		l.lane_comm = nullptr;
+	}
 	// Buffers the caller never released
 	std::vector<const nb200_buf*> leaked(ctx->live.begin(), ctx->live.end());
 	for(const nb200_buf* b : leaked) { nb200_free(ctx, const_cast<nb200_buf*>(b)); }
@@ -477,7 +500,11 @@ NB200_API int nb200_describe(const nb200_ctx* ctx, char* text, size_t text_bytes
 		s += line;
 	}
 	snprintf(line, sizeof(line), "\t precision %s, ranks %d, NCCL %s\n", sizeof(real) == 8 ? "FP64" : "FP32", ctx->nranks,
-			 ctx->comm ? "on" : "off");
+			 ctx->comm ? "on (one process per GPU)" : (ctx->lanes_nccl ? "on (one communicator per lane)" : "off"));
+	s += line;
+	snprintf(line, sizeof(line), "\t shard exchange: %s; solver steps as CUDA graphs: %s\n",
+			 ctx->nshards == 1 ? "none (one shard)" : (ctx->comm || ctx->lanes_nccl ? "NCCL" : (ctx->peer_loads ? "peer copies and peer loads (NVLink)" : "peer copies")),
+			 ctx->sg != nullptr && ctx->sg->mode != SG_OFF ? "on" : (ctx->nshards > 1 ? "off (one shard only)" : "off"));
 	s += line;
 	snprintf(text, text_bytes, "%s", s.c_str());
 	return NB200_OK;
@@ -856,7 +883,7 @@ namespace {
 int sym_tile_edge(const nb200_ctx* ctx)
 {
 	if(ctx->opt_direct_sym == 0) { return 0; }
-	if(ctx->lanes.size() > 1 && (ctx->nranks > 1 || !ctx->peer_loads || ctx->lanes.size() > NB200_SYM_MAX_PEERS)) { return 0; }
+	if(ctx->lanes.size() > 1 && !ctx->lanes_nccl && (ctx->nranks > 1 || !ctx->peer_loads || ctx->lanes.size() > NB200_SYM_MAX_PEERS)) { return 0; }
 	if(ctx->opt_direct_sym < 0 && ctx->n < NB200_SYM_MIN_BODIES) { return 0; }	// too few tiles to fill 148 SMs
 	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(3) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }	// partials > ~30 GB per rank
 	// automatic edge: ~N/128 (>= 8000 equal tiles for N >= 32,768), at most 8192 (192 KB of column sums; scratch
@@ -990,7 +1017,22 @@ int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
 	const size_t	nl = ctx->lanes.size();
 	const unsigned	grid3 = static_cast<unsigned>((3 * ctx->n_shard + 255) / 256);
 	// phase 2: sum the partials of the own shard across shards
-	if(nl > 1)
+	if(nl > 1 && ctx->lanes_nccl)
+	{
+		NC(ctx, ctx->nccl->GroupStart());
+		for(auto& l : ctx->lanes)
+		{
+			ncclResult_t r = ctx->nccl->ReduceScatter(l.sym_acc, l.sym_acc + 3 * ctx->n, 3 * ctx->n_shard, NB200_NCCL_REAL, ncclSum,
+													  static_cast<ncclComm_t>(l.lane_comm), l.stream);
+			if(r != ncclSuccess)
+			{
+				ctx->nccl->GroupEnd();
+				return fail(ctx, NB200_ERR_NCCL, "ncclReduceScatter (lane %d): %s", l.shard, ctx->nccl->GetErrorString(r));
+			}
+		}
+		NC(ctx, ctx->nccl->GroupEnd());
+	}
+	else if(nl > 1)
 	{
 		sym_peers peers;
 		peers.count = static_cast<int>(nl);
@@ -1771,6 +1813,31 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 		sg.pos = sg.seg = sg.seg_start = 0;
 		sg.misses = 0;
 		sg.mode = (value != 0 && can) ? SG_RECORD : SG_OFF;
+	}
+	else if(strcmp(name, "use_nccl") == 0)
+	{
+		// lanes of ONE process exchange shards with NCCL (one communicator per lane) instead of peer copies / peer loads
+		if(value == 0 || ctx->lanes.size() < 2)
+		{
+			ctx->lanes_nccl = false;	// one lane has nothing to exchange; ranks (one process per GPU) always use NCCL
+			return NB200_OK;
+		}
+		if(ctx->lanes_nccl) { return NB200_OK; }
+		std::vector<int> devs;
+		for(auto& l : ctx->lanes)
+		{
+			if(std::find(devs.begin(), devs.end(), l.dev) != devs.end())
+			{
+				return fail(ctx, NB200_ERR_UNSUPPORTED, "use_nccl: the device list repeats device %d (NCCL needs distinct devices); peer copies stay in use", l.dev);
+			}
+			devs.push_back(l.dev);
+		}
+		if(ctx->nccl == nullptr) { ctx->nccl = nccl_load(ctx->err); }
+		if(ctx->nccl == nullptr) { return NB200_ERR_NCCL; }
+		std::vector<ncclComm_t> comms(devs.size(), nullptr);
+		NC(ctx, ctx->nccl->CommInitAll(comms.data(), static_cast<int>(devs.size()), devs.data()));
+		for(size_t i = 0; i < ctx->lanes.size(); ++i) { ctx->lanes[i].lane_comm = comms[i]; }
+		ctx->lanes_nccl = true;
 	}
 	else if(strcmp(name, "direct_targets_per_thread") == 0) { ctx->opt_direct_ipt = value; }
 	else if(strcmp(name, "direct_segments") == 0) { ctx->opt_direct_segments = value; }

@@ -1,7 +1,9 @@
 // nb200 -- NCCL, bound at run time.
 //
 // The library has no link-time NCCL dependency: libnccl.so.2 is dlopen'ed when a
-// context with nranks > 1 is created. Inside a torchrun rank the name resolves to
+// context with nranks > 1 is created, or when a context with several lanes is asked
+// to exchange shards with NCCL (option "use_nccl", the reference's use_nccl=1:
+// ncclCommInitAll over the device list, nbody_engine_cuda.cpp:100-106). Inside a torchrun rank the name resolves to
 // the NCCL build torch already loaded; under a plain C++ host it resolves to the
 // system library. Only the stable v2 entry points are used.
 #ifndef NB200_COMM_CUH
@@ -17,6 +19,9 @@ struct nccl_api
 	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -45,11 +50,14 @@ static nccl_api* nccl_load(std::string& err)
 	api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
 	api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
 	api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+	api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+	api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+	api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
 	api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
 	api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
 	api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(dlsym(h, "ncclReduceScatter"));
 	api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-	if(!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce || !api.ReduceScatter || !api.GetErrorString)
+	if(!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.CommInitAll || !api.GroupStart || !api.GroupEnd || !api.AllGather || !api.AllReduce || !api.ReduceScatter || !api.GetErrorString)
 	{
 		err = "NCCL library lacks a required v2 entry point";
 		dlclose(h);

@@ -64,6 +64,7 @@ struct nb200_lane
 	unsigned long long*	d_scalar = nullptr;	// device scratch (32 x u64): [0] maxabs bits, [2..3] walk counters, [4] probe, [8..15] walk profile
 	unsigned long long*	h_scalar = nullptr;	// pinned mirror
 	bh_state*		bh = nullptr;
+	void*			lane_comm = nullptr;	// ncclComm_t of this lane when the lanes of one process exchange shards with NCCL
 	real*			read_scratch = nullptr;	// [shards][6][n_shard] staging of a multi-rank read_buffer
 	size_t			read_scratch_bytes = 0;
 };
@@ -87,6 +88,7 @@ struct nb200_ctx
 	std::unordered_set<const nb200_buf*>	live;
 	unsigned long long	launches = 0;
 	int			last_direct_path = 0;
+	bool		lanes_nccl = false;	// lanes of one process: NCCL group calls instead of peer copies / peer loads (option use_nccl)
 	bool		peer_loads = true;	// every lane can load from every other lane's memory (same device or peer access enabled)
 	std::string	err;
 	step_graph*	sg = nullptr;	// solver steps as CUDA graphs (nb200_stepgraph.cuh)

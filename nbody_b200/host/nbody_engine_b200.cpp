@@ -54,9 +54,11 @@ struct nbody_engine_b200::data
 	smemory*			m_y;
 	nbody_data*			m_data;
 	bool				m_step_graph;
+	bool				m_use_nccl;
+	int					m_block_size;
 	void*				m_pinned[2];
 	data() : m_force(ef_direct), m_ratio(10), m_tree_build_rate(0), m_tree_layout(etl_heap_stackless),
-		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr), m_step_graph(true)
+		m_device_ids(1, 0), m_ctx(nullptr), m_y(nullptr), m_data(nullptr), m_step_graph(true), m_use_nccl(false), m_block_size(0)
 	{
 		m_pinned[0] = m_pinned[1] = nullptr;
 	}
@@ -152,6 +154,12 @@ bool nbody_engine_b200::ensure_context()
 	if(d->m_step_graph)
 	{
 		d->check(nb200_set_option(d->m_ctx, "step_graph", 1), "step_graph");
+	}
+	if(d->m_use_nccl && d->m_device_ids.size() > 1)
+	{
+		// use_nccl=1 as in the cuda engines (nbody_engine_cuda.cpp:100-106): one communicator per device of this process.
+		// A device list that repeats a device cannot use NCCL; the library says so and keeps its peer copies.
+		d->check(nb200_set_option(d->m_ctx, "use_nccl", 1), "use_nccl");
 	}
 	return true;
 }
@@ -498,6 +506,15 @@ void nbody_engine_b200::print_info() const
 			qDebug() << "\t #" << n << "ID" << d->m_device_ids[n];
 		}
 	}
+	if(d->m_block_size != 0)
+	{
+		qDebug() << "\t" << "block_size:" << d->m_block_size << "(ignored: tile and CTA shapes are chosen by the library)";
+	}
+	qDebug() << "\t" << "use_nccl:" << (d->m_use_nccl ? "1" : "0") << (d->m_device_ids.size() > 1 ? "" : "(one device: nothing to exchange)");
+	if(d->m_step_graph && d->m_device_ids.size() > 1)
+	{
+		qDebug() << "\t" << "step_graph: ignored with several devices";
+	}
 	if(d->m_force == ef_barnes_hut)
 	{
 		qDebug() << "\t" << "distance_to_node_radius_ratio:" << d->m_ratio;
@@ -544,12 +561,17 @@ int nbody_engine_b200::select_devices(const QString& devices_str)
 
 void nbody_engine_b200::set_block_size(int block_size)
 {
-	Q_UNUSED(block_size);
+	// remembered for print_info only: tile and CTA shapes are picked by the library per problem size
+	d->m_block_size = block_size;
 }
 
 void nbody_engine_b200::set_use_nccl(bool active)
 {
-	Q_UNUSED(active);
+	d->m_use_nccl = active;
+	if(d->m_ctx != nullptr && d->m_device_ids.size() > 1)
+	{
+		d->check(nb200_set_option(d->m_ctx, "use_nccl", active ? 1 : 0), "use_nccl");
+	}
 }
 
 void nbody_engine_b200::set_step_graph(bool active)

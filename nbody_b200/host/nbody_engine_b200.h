@@ -62,9 +62,10 @@ public:
 
 	//! Same contract as nbody_engine_cuda::select_devices (nbody_engine_cuda.cpp:576-616): 0 on success
 	int select_devices(const QString& devices_str);
-	//! Kept for factory symmetry with the cuda engines; tile sizes are chosen by the library
+	//! Kept for factory symmetry with the cuda engines; tile sizes are chosen by the library (print_info says so)
 	void set_block_size(int block_size);
-	//! Single-process lanes exchange shards by peer copies; NCCL is used by the one-process-per-GPU mode only
+	//! Several devices in this process: exchange shards with NCCL (ncclCommInitAll, as nbody_engine_cuda.cpp:100-106)
+	//! instead of the default peer copies / peer loads over NVLink
 	void set_use_nccl(bool);
 	//! Solver steps as CUDA graphs (factory parameter step_graph, default on): a step that repeats the previous one call for call
 	//! is replayed as one cudaGraphLaunch from advise_time(); results are those of the eager engine (include/nb200.h)

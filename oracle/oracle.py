@@ -25,6 +25,17 @@ def build(force=False):
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
 
 
+def build_sim():
+    """nbody-simulation in short form with both overlay patches (oracle/_ref/nbody_sim_f{64,32}); links libnb200, so it
+    is built after the kernel libraries. Only where /root/reference is mounted."""
+    if os.path.isdir("/root/reference/nbody"):
+        subprocess.run(["make", "-C", _HERE, "-j8", "sim"], check=True, stdout=subprocess.DEVNULL)
+
+
+def sim_path(precision="f64"):
+    return os.path.join(_HERE, "_ref", "nbody_sim_%s" % precision)
+
+
 def load(precision="f64"):
     if precision in _LIBS:
         return _LIBS[precision]
