@@ -15,11 +15,21 @@
 #include <omp.h>
 #include <stdio.h>
 #include <string.h>
+#include <string>
 
 #include "nbody_solvers.h"
 #include "nbody_engines.h"
 
 namespace {
+//! JSON has no nan / inf: a drift that was never computed (check_step=0) prints as null
+std::string num(double v)
+{
+	char buf[64];
+	if(v != v || v > 1e300 || v < -1e300) { return "null"; }
+	snprintf(buf, sizeof(buf), "%.6e", v);
+	return buf;
+}
+
 QVariantMap parse(int argc, char* argv[])
 {
 	QVariantMap	m;
@@ -116,6 +126,7 @@ int main(int argc, char* argv[])
 	const double	t0 = omp_get_wtime();
 	int				rc = 0;
 	double			t_first = 0;
+	size_t			calls_first = 0;
 	if(max_steps == 0)
 	{
 		rc = solver->run(&data, NULL, max_time, 0, check_step);
@@ -125,6 +136,7 @@ int main(int argc, char* argv[])
 		rc = run_steps(solver.get(), &data, max_time, check_step, 1, param.value("clamp_to_box", false).toBool());
 		engine->get_data(&data);	// blocks until the first step has finished on the device
 		t_first = omp_get_wtime() - t0;
+		calls_first = engine->get_compute_count();
 		if(rc == 0 && max_steps > 1)
 		{
 			rc = run_steps(solver.get(), &data, max_time, check_step, max_steps - 1, param.value("clamp_to_box", false).toBool());
@@ -135,13 +147,13 @@ int main(int argc, char* argv[])
 	if(param.value("json", "0").toInt() != 0)
 	{
 		const size_t steps = data.get_step();
-		printf("{\"engine\": \"%s\", \"solver\": \"%s\", \"bodies\": %zu, \"steps\": %zu, \"fcompute_calls\": %zu, \"time\": %.17g, "
-			   "\"wall_s\": %.6f, \"first_step_s\": %.6f, \"ms_per_step_after_first\": %.6f, \"dP\": %.6e, \"dL\": %.6e, \"dE\": %.6e, \"threads\": %d}\n",
-			   engine->type_name(), solver->type_name(), data.get_count(), steps, engine->get_compute_count(),
+		printf("{\"engine\": \"%s\", \"solver\": \"%s\", \"bodies\": %zu, \"steps\": %zu, \"fcompute_calls\": %zu, \"fcompute_calls_first_step\": %zu, \"time\": %.17g, "
+			   "\"wall_s\": %.6f, \"first_step_s\": %.6f, \"ms_per_step_after_first\": %.6f, \"dP\": %s, \"dL\": %s, \"dE\": %s, \"threads\": %d}\n",
+			   engine->type_name(), solver->type_name(), data.get_count(), steps, engine->get_compute_count(), calls_first,
 			   static_cast<double>(data.get_time()), wall, t_first,
 			   (max_steps > 1 && steps > 1) ? (wall - t_first) * 1e3 / static_cast<double>(steps - 1) : wall * 1e3 / static_cast<double>(steps ? steps : 1),
-			   static_cast<double>(data.get_impulce_err()), static_cast<double>(data.get_impulce_moment_err()),
-			   static_cast<double>(data.get_energy_err()), omp_get_max_threads());
+			   num(static_cast<double>(data.get_impulce_err())).c_str(), num(static_cast<double>(data.get_impulce_moment_err())).c_str(),
+			   num(static_cast<double>(data.get_energy_err())).c_str(), omp_get_max_threads());
 	}
 	solver.reset();	// solvers free their buffers through the engine: before the engine goes
 	return rc;
