@@ -52,9 +52,9 @@ CPU_BUDGET_S = 20.0          # the reference arm stops adding timed steps beyond
 # FMA-pipe instruction slots per pair -- FP64: 18 (the kernel issues 17); FP32: 13 (+1 MUFU on XU)
 SLOTS_PER_PAIR = {"f64": 18, "f32": 13}
 ISSUED_PER_PAIR = {"f64": 17, "f32": 13}
-# Barnes-Hut force evaluation: FP64-pipe instruction slots per accepted (target, node) interaction -- 3 DADD for the
-# separation, 3 for d^2, 11 for the rsqrt refinement, the coefficient and the three accumulating DFMA
-BH_SLOTS_PER_INTERACTION = {"f64": 17, "f32": 13}
+# Barnes-Hut force evaluation: FMA-pipe instruction slots per accepted (target, node) interaction -- 3 DADD for the
+# separation, 3 for d^2, 7 for m r^-3 from the MUFU seed (one series step), three accumulating DFMA
+BH_SLOTS_PER_INTERACTION = {"f64": 16, "f32": 12}
 
 
 def metric_name(workload, precision):
@@ -431,8 +431,10 @@ def direct_block(args, r, world):
 def bh_roofline(args, r, world):
     """The walk against the two pipes that bound it (ncu: DRAM traffic is 0.1 % of HBM, so an HBM fraction says
     nothing; SURVEY 8(d)'s algorithmic bytes are kept as extra keys):
-      fp64 -- accepted (target, node) interactions x 17 FP64-pipe slots / DFMA peak of this run; the decisions
-              themselves are taken in FP32 with a certified margin (FP64 only inside it);
+      fp64 -- accepted (target, node) interactions x 16 FP64-pipe slots / DFMA peak of this run; the decisions
+              themselves are taken in FP32 with a certified margin (FP64 only inside it). The kernel spends these
+              slots on (node, 32-target mask) entries, so masked-out lanes lower the fraction: `lane_use` says by
+              how much (interactions / (32 x entries)), `frac_issued` is the pipe's share including them;
       hbm  -- SURVEY 8(d)'s bytes per visit / interaction against MEASURED_PEAKS.json hbm_gbs (informational)."""
     precision, n = args.precision, r["n"]
     tsz = 8 if precision == "f64" else 4
@@ -444,8 +446,14 @@ def bh_roofline(args, r, world):
     slots = BH_SLOTS_PER_INTERACTION[precision]
     achieved = inter / world * 2 * slots / (force_ms * 1e-3) / 1e12
     peak = fma_peak * 2 / 1e12
+    prof = r.get("walk_profile") or {}
+    entries = prof.get("entries", 0)
     return {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+            "traffic_note": "not measured in this run; the ncu capture of this launch under profiles/ shows DRAM traffic of "
+                            "~0.1 % of HBM peak (the tree is served from L2): the walk is bound by instruction dispatch",
+            "lane_use": (inter / world) / (32.0 * entries) if entries else None,
+            "frac_issued": (32.0 * entries * slots / (force_ms * 1e-3)) / fma_peak if (entries and fma_peak) else None,
             "kernel": "Barnes-Hut walk (all walk launches of one fcompute)", "kernel_ms": force_ms, "phases_ms": r["phases"],
             "node_visits": visits, "interactions": inter, "walk_profile_rank0": r.get("walk_profile"),
             "algorithmic_per_unit": "%d FMA-pipe slots = %d flop per accepted (target, node) interaction; node visits are "

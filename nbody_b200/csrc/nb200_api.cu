@@ -519,12 +519,25 @@ NB200_API int nb200_set_bodies(nb200_ctx* ctx, size_t n, const nb200_real* mass)
 	{
 		return fail(ctx, NB200_ERR_ARG, "set_bodies: N = %zu is not a multiple of the shard count %d", n, ctx->nshards);
 	}
-	if(!ctx->live.empty() && ctx->n != 0 && ctx->n != n)
+	if(ctx->n != 0 && ctx->n != n)
 	{
-		return fail(ctx, NB200_ERR_STATE, "set_bodies: body count changed while buffers are alive");
+		for(const nb200_buf* b : ctx->live)
+		{
+			if(b->sharded) { return fail(ctx, NB200_ERR_STATE, "set_bodies: body count changed while state vectors of the old size are alive"); }
+		}
 	}
 	ctx->n = n;
+	ctx->sym_unavailable = false;
 	ctx->n_shard = n / static_cast<size_t>(ctx->nshards);
+	if(ctx->nshards == 1)
+	{
+		// one shard: a state-sized buffer created before the body count was known has the layout of a state vector anyway
+		for(const nb200_buf* cb : ctx->live)
+		{
+			nb200_buf* b = const_cast<nb200_buf*>(cb);
+			b->sharded = b->bytes == 6 * n * sizeof(real);
+		}
+	}
 	ctx->n_pad = (n + NB200_DIRECT_TILE - 1) / NB200_DIRECT_TILE * NB200_DIRECT_TILE;
 	ctx->n_alloc = (n + 8191) / 8192 * 8192 + 8192;	// room for the zero-mass padding of a last tile of any edge <= 8192
 	for(auto& l : ctx->lanes)
@@ -882,7 +895,7 @@ namespace {
 // Tile edge of the symmetric path for this problem, 0 = use the plain kernel.
 int sym_tile_edge(const nb200_ctx* ctx)
 {
-	if(ctx->opt_direct_sym == 0) { return 0; }
+	if(ctx->opt_direct_sym == 0 || ctx->sym_unavailable) { return 0; }
 	if(ctx->lanes.size() > 1 && !ctx->lanes_nccl && (ctx->nranks > 1 || !ctx->peer_loads || ctx->lanes.size() > NB200_SYM_MAX_PEERS)) { return 0; }
 	if(ctx->opt_direct_sym < 0 && ctx->n < NB200_SYM_MIN_BODIES) { return 0; }	// too few tiles to fill 148 SMs
 	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(3) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }	// partials > ~30 GB per rank
@@ -933,48 +946,71 @@ int sym_launch_default(nb200_ctx* ctx, nb200_lane& l, size_t tiles, size_t smem,
 #endif
 }
 
-// Tiles of shard `l.shard` (dealt round-robin over all shards) -> l.sym_acc = this shard's partial accelerations of
-// ALL bodies, laid out [shard][3][n_shard].
-int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
+size_t sym_lane_tiles(const nb200_ctx* ctx, const nb200_lane& l, int T)
 {
 	const int		S = static_cast<int>((ctx->n + T - 1) / T);
 	const long long	total = static_cast<long long>(S) * (S + 1) / 2;
 	const int		G = ctx->nshards;
-	const size_t	mine = static_cast<size_t>((total - l.shard + G - 1) / G);
+	return static_cast<size_t>((total - l.shard + G - 1) / G);
+}
+
+void sym_lane_release(nb200_lane& l)
+{
+	if(l.sym_tiles) { cudaFree(l.sym_tiles); }
+	if(l.sym_prow) { cudaFree(l.sym_prow); }
+	if(l.sym_pcol) { cudaFree(l.sym_pcol); }
+	if(l.sym_acc) { cudaFree(l.sym_acc); }
+	l.sym_tiles = nullptr;
+	l.sym_prow = l.sym_pcol = l.sym_acc = nullptr;
+	l.sym_edge = 0;
+	l.sym_ntiles = 0;
+}
+
+// Tile list and scratch of one lane for tile edge T (kept until the problem or the edge changes). NB200_ERR_ALLOC when the
+// tile partials (24 N^2 / T bytes over all shards) do not fit next to the caller's buffers.
+int sym_lane_prepare(nb200_ctx* ctx, nb200_lane& l, int T)
+{
+	const int		S = static_cast<int>((ctx->n + T - 1) / T);
+	const int		G = ctx->nshards;
+	const size_t	mine = sym_lane_tiles(ctx, l, T);
 	CU(ctx, cudaSetDevice(l.dev));
-	if(l.sym_edge != T || l.sym_ntiles != mine)
+	if(l.sym_edge == T && l.sym_ntiles == mine) { return NB200_OK; }
+	sym_lane_release(l);
+	std::vector<int2> rc;
+	rc.reserve(mine);
+	long long id = 0;
+	for(int r = 0; r < S; ++r)
 	{
-		if(l.sym_tiles) { cudaFree(l.sym_tiles); }
-		if(l.sym_prow) { cudaFree(l.sym_prow); }
-		if(l.sym_pcol) { cudaFree(l.sym_pcol); }
-		if(l.sym_acc) { cudaFree(l.sym_acc); }
-		l.sym_tiles = nullptr;
-		l.sym_prow = l.sym_pcol = l.sym_acc = nullptr;
-		l.sym_edge = 0;
-		std::vector<int2> rc;
-		rc.reserve(mine);
-		long long id = 0;
-		for(int r = 0; r < S; ++r)
+		for(int c = r; c < S; ++c, ++id)
 		{
-			for(int c = r; c < S; ++c, ++id)
-			{
-				if(id % G == l.shard) { rc.push_back(make_int2(r, c)); }
-			}
+			if(id % G == l.shard) { rc.push_back(make_int2(r, c)); }
 		}
-		const size_t tile_bytes = 3 * static_cast<size_t>(T) * sizeof(real);
-		if(cudaMalloc(&l.sym_tiles, std::max<size_t>(1, mine) * sizeof(int2)) != cudaSuccess ||
-		   cudaMalloc(&l.sym_prow, std::max<size_t>(1, mine) * tile_bytes) != cudaSuccess ||
-		   cudaMalloc(&l.sym_pcol, std::max<size_t>(1, mine) * tile_bytes) != cudaSuccess ||
-		   cudaMalloc(&l.sym_acc, (3 * ctx->n + 3 * ctx->n_shard) * sizeof(real)) != cudaSuccess)
-		{
-			cudaGetLastError();
-			return fail(ctx, NB200_ERR_ALLOC, "fcompute_direct: symmetric-tile scratch allocation failed (%zu tiles of %d)", mine, T);
-		}
-		CU(ctx, cudaMemcpyAsync(l.sym_tiles, rc.data(), mine * sizeof(int2), cudaMemcpyHostToDevice, l.stream));
-		CU(ctx, cudaStreamSynchronize(l.stream));
-		l.sym_edge = T;
-		l.sym_ntiles = mine;
 	}
+	const size_t tile_bytes = 3 * static_cast<size_t>(T) * sizeof(real);
+	if(cudaMalloc(&l.sym_tiles, std::max<size_t>(1, mine) * sizeof(int2)) != cudaSuccess ||
+	   cudaMalloc(&l.sym_prow, std::max<size_t>(1, mine) * tile_bytes) != cudaSuccess ||
+	   cudaMalloc(&l.sym_pcol, std::max<size_t>(1, mine) * tile_bytes) != cudaSuccess ||
+	   cudaMalloc(&l.sym_acc, (3 * ctx->n + 3 * ctx->n_shard) * sizeof(real)) != cudaSuccess)
+	{
+		cudaGetLastError();
+		sym_lane_release(l);
+		return fail(ctx, NB200_ERR_ALLOC, "fcompute_direct: symmetric-tile scratch allocation failed (%zu tiles of %d)", mine, T);
+	}
+	CU(ctx, cudaMemcpyAsync(l.sym_tiles, rc.data(), mine * sizeof(int2), cudaMemcpyHostToDevice, l.stream));
+	CU(ctx, cudaStreamSynchronize(l.stream));
+	l.sym_edge = T;
+	l.sym_ntiles = mine;
+	return NB200_OK;
+}
+
+// Tiles of shard `l.shard` (dealt round-robin over all shards) -> l.sym_acc = this shard's partial accelerations of
+// ALL bodies, laid out [shard][3][n_shard]. The lane's scratch is in place (sym_lane_prepare).
+int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
+{
+	const int		S = static_cast<int>((ctx->n + T - 1) / T);
+	const int		G = ctx->nshards;
+	const size_t	mine = l.sym_ntiles;
+	CU(ctx, cudaSetDevice(l.dev));
 	if(ctx->opt_timing) { CU(ctx, cudaEventRecord(l.ev_t[2], l.stream)); }
 	const size_t smem = 3 * static_cast<size_t>(T) * sizeof(real);
 	if(mine > 0)
@@ -1006,9 +1042,46 @@ int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
 
 int sym_fcompute(nb200_ctx* ctx, const nb200_buf* y, nb200_buf* f, int T)
 {
-	// phase 1: every lane turns its tiles into a partial acceleration vector over all bodies. A failed scratch
-	// allocation on a later lane only wastes the earlier lanes' launches: the caller reruns the step with the
-	// ordered-pair kernel, which overwrites f completely.
+	// phase 0: scratch. Whether the symmetric path runs must be ONE decision for all shards: a rank that fell back alone
+	// would leave the others waiting in ncclReduceScatter. Scratch is (re)allocated at the same call on every rank (same
+	// N, edge and options everywhere), so that call ends with a min-all-reduce of "it fits here"; if it does not fit
+	// somewhere, everybody releases the scratch and takes the ordered-pair kernel.
+	bool	fresh = false;
+	int		fits = 1;
+	for(auto& l : ctx->lanes)
+	{
+		fresh = fresh || l.sym_edge != T || l.sym_ntiles != sym_lane_tiles(ctx, l, T);
+	}
+	if(fresh)
+	{
+		for(auto& l : ctx->lanes)
+		{
+			int rc = sym_lane_prepare(ctx, l, T);
+			if(rc == NB200_ERR_ALLOC) { fits = 0; break; }
+			if(rc != NB200_OK) { return rc; }
+		}
+		if(ctx->nranks > 1)
+		{
+			nb200_lane& l = ctx->lanes[0];
+			CU(ctx, cudaSetDevice(l.dev));
+			l.h_scalar[6] = static_cast<unsigned long long>(fits);
+			CU(ctx, cudaMemcpyAsync(l.d_scalar + 6, l.h_scalar + 6, sizeof(unsigned long long), cudaMemcpyHostToDevice, l.stream));
+			NC(ctx, ctx->nccl->AllReduce(l.d_scalar + 6, l.d_scalar + 6, 1, ncclUint64, ncclMin, static_cast<ncclComm_t>(ctx->comm), l.stream));
+			CU(ctx, cudaMemcpyAsync(l.h_scalar + 6, l.d_scalar + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+			CU(ctx, cudaStreamSynchronize(l.stream));
+			fits = static_cast<int>(l.h_scalar[6]);
+		}
+		if(!fits)
+		{
+			for(auto& l : ctx->lanes)
+			{
+				cudaSetDevice(l.dev);
+				sym_lane_release(l);
+			}
+			return fail(ctx, NB200_ERR_ALLOC, "fcompute_direct: symmetric-tile scratch does not fit on every shard");
+		}
+	}
+	// phase 1: every lane turns its tiles into a partial acceleration vector over all bodies
 	for(auto& l : ctx->lanes)
 	{
 		int rc = sym_lane_partials(ctx, l, T);
@@ -1117,8 +1190,11 @@ NB200_API int nb200_fcompute_direct(nb200_ctx* ctx, const nb200_buf* y, nb200_bu
 		ctx->last_direct_path = edge;
 		rc = sym_fcompute(ctx, y, f, edge);
 		if(rc != NB200_ERR_ALLOC) { return rc; }
-		// the tile partials (24 N^2 / T bytes) did not fit next to the caller's buffers: ordered-pair kernel from now on
-		ctx->opt_direct_sym = 0;
+		// the tile partials (24 N^2 / T bytes) did not fit next to the caller's buffers on some shard: ordered-pair kernel for
+		// this body set from now on, on every shard alike (sym_fcompute agreed on it). Scratch is only ever (re)allocated by
+		// the first fcompute after set_bodies or an option change -- both empty the step table, and the step after that runs
+		// eagerly -- so no recorded step or graph describes the path given up here.
+		ctx->sym_unavailable = true;
 	}
 	ctx->last_direct_path = 0;
 
@@ -1483,7 +1559,9 @@ NB200_API int nb200_fmaxabs(nb200_ctx* ctx, const nb200_buf* a, nb200_real* resu
 		nb200_lane& l = ctx->lanes[i];
 		CU(ctx, cudaSetDevice(l.dev));
 		CU(ctx, cudaMemsetAsync(l.d_scalar, 0, sizeof(unsigned long long), l.stream));
-		ew_maxabs<<<ew_grid(l, a->lane_elems), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), a->lane_elems, l.d_scalar);
+		// element 0 of the vector lives on shard 0 (sharded buffers) or on every lane alike (replicated ones)
+		ew_maxabs<<<ew_grid(l, a->lane_elems), NB200_EW_THREADS, 0, l.stream>>>(lane_ptr(a, i), a->lane_elems, l.d_scalar,
+																				 (!a->sharded || l.shard == 0) ? 1 : 0);
 		LAUNCHED(ctx);
 		if(ctx->nranks > 1)
 		{
@@ -1844,7 +1922,7 @@ NB200_API int nb200_set_option(nb200_ctx* ctx, const char* name, long long value
 	else if(strcmp(name, "walk_mode") == 0) { ctx->opt_walk_mode = value; }	// 0 = automatic, 1 = thread per target, 2 / 4 = targets per lane, 32 = one per lane
 	else if(strcmp(name, "walk_threads") == 0) { ctx->opt_walk_threads = value; }
 	else if(strcmp(name, "walk_lpt") == 0) { ctx->opt_walk_lpt = value; }	// -1 automatic, 0 off, 1 on
-	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; }	// -1 auto, 0 off, 1 on
+	else if(strcmp(name, "direct_symmetric") == 0) { ctx->opt_direct_sym = value; ctx->sym_unavailable = false; }	// -1 auto, 0 off, 1 on
 	else if(strcmp(name, "direct_small") == 0) { ctx->opt_direct_small = value; }	// -1 auto (N <= 4096), 0 off, 1 on
 	else if(strcmp(name, "direct_sym_tile") == 0) { ctx->opt_sym_tile = value; }
 	else if(strcmp(name, "direct_sym_shape") == 0) { ctx->opt_sym_shape = value; }

@@ -88,6 +88,7 @@ struct nb200_ctx
 	std::unordered_set<const nb200_buf*>	live;
 	unsigned long long	launches = 0;
 	int			last_direct_path = 0;
+	bool		sym_unavailable = false;	// the symmetric tiles' scratch did not fit on some shard: ordered pairs until the body set changes
 	bool		lanes_nccl = false;	// lanes of one process: NCCL group calls instead of peer copies / peer loads (option use_nccl)
 	bool		peer_loads = true;	// every lane can load from every other lane's memory (same device or peer access enabled)
 	std::string	err;

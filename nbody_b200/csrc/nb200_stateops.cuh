@@ -185,9 +185,12 @@ __global__ void __launch_bounds__(NB200_EW_THREADS) ew_fmaddn_corr(real* a, real
 
 // max |a[i]| as an integer max over IEEE bit patterns of |a| (order-preserving for
 // non-negative values, so the result is exact and independent of reduction order).
-// NaNs are ignored, as the reference's `v > result` comparison ignores them.
+// NaNs are ignored, as the reference's `v > result` comparison ignores them -- except in element 0 of the whole
+// vector, which seeds the reference's loop (result = fabs(a[0]), nbody_engine_openmp.cpp:284): a NaN there is the
+// result, so an adaptive run that blew up takes the same accept / subdivide path as on the CPU engines. seed_first is
+// set for the shard that holds element 0; a NaN's bit pattern is larger than any number's, so it survives every max.
 __global__ void __launch_bounds__(NB200_EW_THREADS) ew_maxabs(const real* __restrict__ a, size_t count,
-															   unsigned long long* __restrict__ result_bits)
+															   unsigned long long* __restrict__ result_bits, int seed_first)
 {
 	NB200_EW_LOOP(count)
 	ubits_t m = 0;
@@ -197,13 +200,13 @@ __global__ void __launch_bounds__(NB200_EW_THREADS) ew_maxabs(const real* __rest
 #pragma unroll
 		for(int l = 0; l < NB200_VEC; ++l)
 		{
-			if(va.v[l] == va.v[l]) { ubits_t b = abs_bits(va.v[l]); m = b > m ? b : m; }
+			if(va.v[l] == va.v[l] || (seed_first && v == 0 && l == 0)) { ubits_t b = abs_bits(va.v[l]); m = b > m ? b : m; }
 		}
 	}
 	for(size_t i = nvec * NB200_VEC + gid; i < count; i += stride)
 	{
 		real x = a[i];
-		if(x == x) { ubits_t b = abs_bits(x); m = b > m ? b : m; }
+		if(x == x || (seed_first && i == 0)) { ubits_t b = abs_bits(x); m = b > m ? b : m; }
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1)

@@ -2,6 +2,7 @@
 
 #include <QDebug>
 #include <algorithm>
+#include <stdlib.h>
 
 #include "nb200.h"
 
@@ -101,11 +102,18 @@ struct nbody_engine_b200::data
 		}
 		return s->buf();
 	}
+	//! Argument errors are logged and the call returns, as every reference engine does; a CUDA or NCCL runtime error
+	//! ends the program like the cuda engines' check macros (nbody_engine_cuda.cpp:8-24: qDebug + exit(3)) -- a solver
+	//! must not go on integrating with an f nobody wrote. (The library itself never exits: that choice is the host's.)
 	void check(int rc, const char* what) const
 	{
 		if(rc != NB200_OK)
 		{
 			qDebug() << what << nb200_last_error(m_ctx);
+		}
+		if(rc == NB200_ERR_CUDA || rc == NB200_ERR_NCCL)
+		{
+			exit(3);
 		}
 	}
 };
@@ -172,12 +180,22 @@ bool nbody_engine_b200::init(nbody_data* body_data)
 	}
 	d->m_data = body_data;
 	size_t	count = body_data->get_count();
+	if(d->m_force == ef_barnes_hut && (count & (count - 1)) != 0)
+	{
+		// The kd-heap keeps its leaves at [N, 2N): in bounds only for N = 2^k. The reference sizes its arrays 2N all the
+		// same (nbody_space_heap.cpp:24) and overruns them for any other N; here such a body set is refused up front.
+		qDebug() << "b200_bh needs a power-of-two body count (kd-heap layout), got" << count;
+		return false;
+	}
+	// a re-init with another body count: the old state vector goes first (the library refuses to change N under live
+	// state vectors of the old size)
+	delete d->m_y;
+	d->m_y = nullptr;
 	if(nb200_set_bodies(d->m_ctx, count, body_data->get_mass()) != NB200_OK)
 	{
 		qDebug() << "nb200_set_bodies" << nb200_last_error(d->m_ctx);
 		return false;
 	}
-	delete d->m_y;
 	d->m_y = dynamic_cast<smemory*>(create_buffer(sizeof(nbcoord_t) * problem_size()));
 	if(d->m_y == nullptr)
 	{

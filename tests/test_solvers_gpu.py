@@ -89,6 +89,28 @@ def test_euler_golden_on_engine_variants(ref64, adapter, kw):
     assert ok, "max |dy| = %g" % err
 
 
+def test_adapter_reinit_with_another_body_count_and_early_buffers(ref64, adapter):
+    """init() again with a different N (the old state vector is released first), and a buffer created BEFORE the first
+    init (ensure_context) that is used as f afterwards."""
+    from oracle import refharness as R
+    e = b200_engine(ref64, adapter, engine="b200")
+    early = e.create_buffer(6 * 128 * 8)
+    for stars in (64, 128):
+        d = R.Data(ref64).make_universe(stars)
+        ref = R.Engine(ref64, engine="simple")
+        assert ref.init(d) and e.init(d)
+        want = ref.fcompute_y()
+        got = e.fcompute_y()
+        assert np.abs(got - want).max() <= 1e-13
+        if stars == 64:
+            e.fcompute(0.0, e.get_y(), early)
+            assert np.array_equal(e.read_buffer(early), got)
+            e.free_buffer(early)
+        ref.close()
+        d.close()
+    e.close()
+
+
 def test_factory_rejects_bad_parameters(ref64, adapter):
     from oracle import refharness as R
     for bad in ("", "a", "0,a", "-1", "9999"):

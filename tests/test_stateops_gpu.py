@@ -293,3 +293,49 @@ def test_invalid_device_strings():
             Engine(devices=bad)
     with pytest.raises(ValueError):
         Engine(kind="bh", tree_layout="tree")
+
+
+@pytest.mark.parametrize("devices", ["0", "0,0"])
+def test_fmaxabs_nan_follows_the_reference_loop(ref64, devices):
+    """fmaxabs of the reference: result = fabs(a[0]); then `if(v > result)` over all elements
+    (nbody_engine_openmp.cpp:284-296). A NaN in element 0 therefore IS the result, a NaN anywhere else is skipped --
+    the engine does the same on every shard layout, so a run that blew up branches as it does on the CPU engines."""
+    from nbody_b200 import Engine
+    from oracle import refharness as R
+    g = load_golden_npz("g1_n128")
+    n6 = 6 * 128
+    d = R.Data(ref64).import_(g["y"], g["mass"])
+    cpu = R.Engine(ref64, engine="simple")
+    assert cpu.init(d)
+    with Engine(devices=devices) as e:
+        assert e.init(g["y"], g["mass"])
+        buf = e.create_buffer(n6 * 8)
+        for where in (None, 0, 1, n6 // 2, n6 - 1):
+            a = np.linspace(-3.0, 2.0, n6)
+            if where is not None:
+                a[where] = np.nan
+            e.write_buffer(buf, a)
+            got = e.fmaxabs(buf)
+            m = cpu.new_buffer(a)
+            want = cpu.fmaxabs(m)
+            cpu.free_buffer(m)
+            assert (np.isnan(got) and np.isnan(want)) or got == want, (where, got, want)
+            assert np.isnan(got) == (where == 0)
+    cpu.close()
+    d.close()
+
+
+def test_state_sized_buffer_created_before_the_bodies_are_known():
+    """One shard: a buffer of 6N reals allocated before set_bodies / init has the layout of a state vector and is
+    accepted as one afterwards (the adapter allows create_buffer before init)."""
+    from nbody_b200 import Engine
+    g = load_golden_npz("g1_n128")
+    with Engine() as e:
+        early = e.create_buffer(6 * 128 * 8)
+        assert e.init(g["y"], g["mass"])
+        e.fcompute(0.0, e.get_y(), early)
+        late = e.create_buffer(6 * 128 * 8)
+        e.fcompute(0.0, e.get_y(), late)
+        assert np.array_equal(e.read_buffer(early), e.read_buffer(late))
+        e.fmadd_inplace(early, late, 1.0)
+        assert np.array_equal(e.read_buffer(early), 2 * e.read_buffer(late))
