@@ -399,17 +399,17 @@ def direct_block(args, r, world):
     sym_edge = r["path"]
     kernel = "direct_small" if sym_edge < 0 else "direct_pairs"
     if sym_edge > 0:
-        # symmetric tiles: 21 FP64-pipe (16 FP32-pipe) instructions per UNORDERED pair = 10.5 (8) per interaction
-        issued = 10.5 if precision == "f64" else 4   # FP32: 16 packed two-wide instructions per 2 unordered pairs
-        kernel = "%s (tile edge %d)" % ("direct_sym_tiles<4,2>" if precision == "f64" else "direct_sym_tiles_f32x2<8>", sym_edge)
+        # symmetric tiles: 20 FP64-pipe (16 FP32-pipe) instructions per UNORDERED pair = 10 (8) per interaction
+        issued = 10 if precision == "f64" else 4     # FP32: 16 packed two-wide instructions per 2 unordered pairs
+        kernel = "%s (tile edge %d)" % ("direct_sym_tiles<8,1>" if precision == "f64" else "direct_sym_tiles_f32x2<8>", sym_edge)
     achieved = pairs_per_launch * 2 * slots / (force_ms * 1e-3) / 1e12
     peak = fma_peak * 2 / 1e12
     roofline = {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": None,
                 "traffic_note": "not measured in this run (a number taken under ncu is never a bench value); one ncu --set full capture "
-                                "of this launch is committed under profiles/ (r1_ncu_direct_sym_tiles_n1m.csv: 0.31 GB read + 3.21 GB "
-                                "written per launch, the tile partials; the kernel is FP64-pipe bound, DRAM is at 4 GB/s)",
+                                "of this launch is committed under profiles/ (r2_ncu_direct_sym_tiles_n1m.csv; round 1's capture: 0.31 GB read + "
+                                "3.21 GB written per launch, the tile partials; the kernel is FP64-pipe bound, DRAM is at 4 GB/s)",
                 "kernel": kernel, "kernel_ms": force_ms,
                 "algorithmic_per_unit": "%d FMA-pipe slots = %d flop per pair interaction (SURVEY 8d); kernel issues %g per interaction%s"
                                         % (slots, 2 * slots, issued,

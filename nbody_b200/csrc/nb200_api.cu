@@ -939,10 +939,11 @@ int sym_launch_default(nb200_ctx* ctx, nb200_lane& l, size_t tiles, size_t smem,
 	if(row_blocks >= 2) { return sym_launch(ctx, l, direct_sym_tiles_f32x2<8, false, 2>, tiles, smem, T, 2); }
 	return sym_launch(ctx, l, direct_sym_tiles_f32x2<8, false, 1>, tiles, smem, T, 1);
 #else
-	const int row_blocks = T / 128;	// direct_sym_tiles<4, 2>
-	if(row_blocks >= 8) { return sym_launch(ctx, l, direct_sym_tiles<4, 2, true, 8>, tiles, smem, T, 8); }
-	if(row_blocks >= 4) { return sym_launch(ctx, l, direct_sym_tiles<4, 2, true, 4>, tiles, smem, T, 4); }
-	return sym_launch(ctx, l, direct_sym_tiles<4, 2, true, 2>, tiles, smem, T, 2);
+	const int row_blocks = T / 256;	// direct_sym_tiles<8, 1>
+	if(row_blocks >= 8) { return sym_launch(ctx, l, direct_sym_tiles<8, 1, true, 8>, tiles, smem, T, 8); }
+	if(row_blocks >= 4) { return sym_launch(ctx, l, direct_sym_tiles<8, 1, true, 4>, tiles, smem, T, 4); }
+	if(row_blocks >= 2) { return sym_launch(ctx, l, direct_sym_tiles<8, 1, true, 2>, tiles, smem, T, 2); }
+	return sym_launch(ctx, l, direct_sym_tiles<8, 1, true, 1>, tiles, smem, T, 1);
 #endif
 }
 
@@ -1026,9 +1027,7 @@ int sym_lane_partials(nb200_ctx* ctx, nb200_lane& l, int T)
 		case 6: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2, false>, mine, smem, T); break;	// each column body shuffled right after its pairs (A/B: slower)
 		case 3: rc = sym_launch(ctx, l, direct_sym_tiles<4, 4>, mine, smem, T); break;
 		case 2: rc = sym_launch(ctx, l, direct_sym_tiles<8, 2>, mine, smem, T); break;
-#if NB200_PRECISION == 1
-		case 1: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2>, mine, smem, T); break;	// scalar FP32 arithmetic
-#endif
+		case 1: rc = sym_launch(ctx, l, direct_sym_tiles<4, 2>, mine, smem, T); break;	// FP64: round 1's default; FP32: scalar arithmetic
 		default: rc = sym_launch(ctx, l, direct_sym_tiles<8, 1>, mine, smem, T); break;
 		}
 		if(rc != NB200_OK) { return rc; }

@@ -109,8 +109,8 @@ struct nb200_ctx
 	long long	opt_direct_small = -1;	// single-launch kernel for small systems: -1 auto (N <= 4096, one shard), 0 off, 1 force
 	long long	opt_sym_tile = 0;		// tile edge override (multiple of 256)
 	// bodies per lane (row x column): 0: 8 x 1, 1: 4 x 2, 2: 8 x 2, 3: 4 x 4; FP32 only: 4: 8 x 2 packed f32x2, 5: 4 x 2 packed.
-	// Fastest measured: 4 x 2 (FP64), 8 x 2 packed (FP32)
-	long long	opt_sym_shape = sizeof(real) == 8 ? 1 : 4;
+	// Fastest measured: 8 x 1 (FP64, with the clamp-free pass), 8 x 2 packed (FP32)
+	long long	opt_sym_shape = sizeof(real) == 8 ? 0 : 4;
 };
 
 struct nb200_buf

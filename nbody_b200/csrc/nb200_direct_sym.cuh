@@ -26,12 +26,13 @@
 
 #define NB200_SYM_WARPS 8
 #define NB200_SYM_THREADS (32 * NB200_SYM_WARPS)
-// direct_sym_shape of the kernel this build uses by default: FP64 1 = <4, 2> (4 row x 2 column bodies per lane),
-// FP32 4 = packed f32x2 with 8 row bodies; automatic from this many bodies on
+// direct_sym_shape of the kernel this build uses by default: FP64 0 = <8, 1> (8 row bodies x 1 column body per lane: one
+// column body's 7 values are the only shuffles of a step; N = 1M on one B200 with the clamp-free pass: <8,1> 761 ms,
+// <4,2> 800 ms, <8,2> 870 ms, <4,4> 961 ms), FP32 4 = packed f32x2 with 8 row bodies
 #if NB200_PRECISION == 1
 #define NB200_SYM_DEFAULT_SHAPE 4
 #else
-#define NB200_SYM_DEFAULT_SHAPE 1
+#define NB200_SYM_DEFAULT_SHAPE 0
 #endif
 // measured on one B200 (profiles/r1_direct_sizes.json): FP64 N = 8,192: 5.0e11 (ordered pairs) vs 6.0e11 pairs/s, FP32
 // N = 8,192: 9.4e11 vs 8.5e11, N = 16,384: 1.53e12 vs 1.57e12
@@ -48,25 +49,47 @@ __device__ __forceinline__ double sym_shfl(double v, int src_lane)
 	int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src_lane);
 	return __hiloint2double(hi, lo);
 }
-// one unordered pair: d = column - row; both accumulator sets updated (21 FP64-pipe instructions)
+// one unordered pair: d = column - row; both accumulator sets updated: 20 FP64-pipe instructions (3 for d, 3 for r^2,
+// 6 for r^-3 from the MUFU seed in one series step -- y0^3 (1 + e (3/2 + 15/8 e)), e = 1 - r^2 y0^2 exact to one rounding
+// because the seed has 21 significant bits; truncation error 35/16 e^3 < 2^-56 --, 2 for the mass products, 6 DFMA).
+// On this pipe an FP64 instruction holds the dispatch port for two cycles and every other instruction for one
+// (profiles/microbench/bh_sum_loop.cu), so the integer clamp of r^2 (4 instructions) is worth 10 % of a pair:
+// CLAMP = false leaves it out and records the smallest high word of r^2 in `low` instead (1 instruction); the tile is
+// redone with the clamp if any pair of it came closer than MinDistance (sym_tile below).
+template<bool CLAMP>
 __device__ __forceinline__ void sym_pair(double dx, double dy, double dz, double m_row, double m_col,
-										 double& ax, double& ay, double& az, double& bx, double& by, double& bz)
+										 double& ax, double& ay, double& az, double& bx, double& by, double& bz, int& low)
 {
 	double	r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-	long long		bits = __double_as_longlong(r2);
-	const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8, exact clamp on the integer pipe
-	bits = bits < min_bits ? min_bits : bits;
-	r2 = __longlong_as_double(bits);
+	if(CLAMP)
+	{
+		long long		bits = __double_as_longlong(r2);
+		const long long	min_bits = 0x3E45798EE2308C3ALL;	// 1e-8, exact clamp on the integer pipe
+		bits = bits < min_bits ? min_bits : bits;
+		r2 = __longlong_as_double(bits);
+	}
+	else
+	{
+		low = min(low, __double2hiint(r2));	// r2 >= 0: the high word orders like the value
+	}
 	double	y0;
 	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
-	double	h = r2 * y0;
-	double	e = fma(-h, y0, 1.0);
-	double	pp = fma(e, 0.375, 0.5);
-	double	qq = y0 * e;
-	double	y = fma(qq, pp, y0);
-	double	y3 = (y * y) * y;
-	double	ca = m_col * y3;
-	double	cb = m_row * y3;
+#ifdef NB200_SYM_NEWTON
+	const double	h = r2 * y0;
+	const double	e = fma(-h, y0, 1.0);
+	const double	pp = fma(e, 0.375, 0.5);
+	const double	qq = y0 * e;
+	const double	y = fma(qq, pp, y0);
+	const double	y3 = (y * y) * y;
+#else
+	const double	y2 = y0 * y0;
+	const double	e = fma(-r2, y2, 1.0);
+	const double	u = e * fma(e, 1.875, 1.5);
+	const double	s3 = y0 * y2;
+	const double	y3 = fma(s3, u, s3);
+#endif
+	const double	ca = m_col * y3;
+	const double	cb = m_row * y3;
 	ax = fma(dx, ca, ax);
 	ay = fma(dy, ca, ay);
 	az = fma(dz, ca, az);
@@ -74,15 +97,18 @@ __device__ __forceinline__ void sym_pair(double dx, double dy, double dz, double
 	by = fma(-dy, cb, by);
 	bz = fma(-dz, cb, bz);
 }
+#define NB200_SYM_CLOSE_HI 0x3E45798E	// high word of 1e-8: a pair whose r^2 has a high word <= this may need the clamp
 #else
 __device__ __forceinline__ float sym_shfl(float v, int src_lane)
 {
 	return __shfl_sync(0xffffffffu, v, src_lane);
 }
-// FP32: 16 FP32-pipe instructions + MUFU.RSQ + FMNMX per unordered pair
+// FP32: 16 FP32-pipe instructions + MUFU.RSQ + FMNMX per unordered pair (the clamp is one instruction: always on)
+template<bool CLAMP>
 __device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_row, float m_col,
-										 float& ax, float& ay, float& az, float& bx, float& by, float& bz)
+										 float& ax, float& ay, float& az, float& bx, float& by, float& bz, int& low)
 {
+	(void)low;
 	float	r2 = fmaxf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), NB200_MIN_DISTANCE);
 	float	y = rsqrtf(r2);
 	float	y3 = (y * y) * y;
@@ -110,12 +136,12 @@ __device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_r
 // tile edge 4096 with this kernel: 846 ms, but twice the partial-sum scratch.
 // WARPS: warps per CTA. A tile needs T / (32 I) row blocks; with fewer than 8 of them (small tiles for small N) the
 // CTA shrinks instead of leaving warps idle, and several CTAs share an SM (230 registers x 128 threads fit twice).
-template<int I, int J, bool LATE_SHUFFLES = true, int WARPS = NB200_SYM_WARPS>
-__global__ void __launch_bounds__(32 * WARPS, NB200_SYM_MINB)
-direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, real* __restrict__ p_row,
-				 real* __restrict__ p_col, int tile_edge)
+// One tile, with or without the clamp of r^2. Returns (CLAMP = false) the smallest high word of r^2 this thread saw.
+template<int I, int J, bool LATE_SHUFFLES, int WARPS, bool CLAMP>
+__device__ __forceinline__ int sym_tile(const body4* __restrict__ src, const int2* __restrict__ tile_rc, real* __restrict__ p_row,
+										 real* __restrict__ p_col, int tile_edge, real* colacc)
 {
-	extern __shared__ real colacc[];	// [3][tile_edge]
+	int			low = 0x7fffffff;
 	const int	T = tile_edge;
 	const int	lane = threadIdx.x & 31;
 	const int	warp = threadIdx.x >> 5;
@@ -189,8 +215,8 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 #pragma unroll
 					for(int k = 0; k < I; ++k)
 					{
-						sym_pair(xb[q] - xa[k], yb[q] - ya[k], zb[q] - za[k], ma[k], mb[q],
-								 ax[k], ay[k], az[k], bx[q], by[q], bz[q]);
+						sym_pair<CLAMP>(xb[q] - xa[k], yb[q] - ya[k], zb[q] - za[k], ma[k], mb[q],
+										ax[k], ay[k], az[k], bx[q], by[q], bz[q], low);
 					}
 					if(!LATE_SHUFFLES)
 					{
@@ -242,6 +268,30 @@ direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc
 	{
 		out_col[e] = colacc[e];
 	}
+	return low;
+}
+
+#ifndef NB200_SYM_FAST
+#define NB200_SYM_FAST 1	// 0: always clamp (A/B)
+#endif
+template<int I, int J, bool LATE_SHUFFLES = true, int WARPS = NB200_SYM_WARPS>
+__global__ void __launch_bounds__(32 * WARPS, NB200_SYM_MINB)
+direct_sym_tiles(const body4* __restrict__ src, const int2* __restrict__ tile_rc, real* __restrict__ p_row,
+				 real* __restrict__ p_col, int tile_edge)
+{
+	extern __shared__ real colacc[];	// [3][tile_edge]
+#if NB200_PRECISION == 2
+	// A diagonal tile holds every body's pair with itself (r^2 = 0): clamp from the start. Any other tile runs without
+	// the clamp and is redone with it if some pair came closer than MinDistance (1e-4): exact either way, and rare --
+	// nothing of the first pass is kept (row and column sums are overwritten, the column sums in shared memory reset).
+	const int2	rc = tile_rc[blockIdx.x];
+	if(NB200_SYM_FAST && rc.x != rc.y)
+	{
+		const int low = sym_tile<I, J, LATE_SHUFFLES, WARPS, false>(src, tile_rc, p_row, p_col, tile_edge, colacc);
+		if(__syncthreads_or(low <= NB200_SYM_CLOSE_HI) == 0) { return; }
+	}
+#endif
+	sym_tile<I, J, LATE_SHUFFLES, WARPS, true>(src, tile_rc, p_row, p_col, tile_edge, colacc);
 }
 
 #if NB200_PRECISION == 1
