@@ -407,9 +407,11 @@ def direct_block(args, r, world):
     roofline = {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": None,
-                "traffic_note": "not measured in this run (a number taken under ncu is never a bench value); one ncu --set full capture "
-                                "of this launch is committed under profiles/ (r2_ncu_direct_sym_tiles_n1m.csv; round 1's capture: 0.31 GB read + "
-                                "3.21 GB written per launch, the tile partials; the kernel is FP64-pipe bound, DRAM is at 4 GB/s)",
+                "traffic_note": "DRAM bytes cannot be measured in a timed run (ncu serialises and replays); `traffic` is the "
+                                "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this very launch, "
+                                "committed as profiles/r2_ncu_direct_sym_tiles_n1m.csv, and only filled in when this run is that "
+                                "launch (N = 1M, one GPU, FP64, default kernel); it is the tile partials (24 N^2 / T bytes) -- the "
+                                "kernel is FP64-pipe bound and DRAM runs at ~5 GB/s",
                 "kernel": kernel, "kernel_ms": force_ms,
                 "algorithmic_per_unit": "%d FMA-pipe slots = %d flop per pair interaction (SURVEY 8d); kernel issues %g per interaction%s"
                                         % (slots, 2 * slots, issued,
@@ -418,6 +420,9 @@ def direct_block(args, r, world):
                 "frac_issued": (pairs_per_launch * issued / (force_ms * 1e-3)) / fma_peak if fma_peak else None,
                 "peak_source": "nb200_probe_fma_peak (FMA chain kernel of this precision, this run); MEASURED_PEAKS.json has no "
                                "FP64/FP32 vector entry; nominal 148 SM x 64 (FP64) / 128 (FP32) FMA/clk x 1.965 GHz = 37.2 / 74.4 TFLOP/s"}
+    if sym_edge == 8192 and n == N_DIRECT and world == 1 and precision == "f64" and not args.opt:
+        roofline["traffic"] = 3.537e9      # 0.325 GB read + 3.212 GB written per launch
+        roofline["traffic_source"] = "profiles/r2_ncu_direct_sym_tiles_n1m.csv"
     e2e_obj = None
     if r["e2e"]:
         e = r["e2e"]
@@ -449,9 +454,12 @@ def bh_roofline(args, r, world):
     prof = r.get("walk_profile") or {}
     entries = prof.get("entries", 0)
     return {"bound": "fp64_fma_pipe" if precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
-            "traffic_note": "not measured in this run; the ncu capture of this launch under profiles/ shows DRAM traffic of "
-                            "~0.1 % of HBM peak (the tree is served from L2): the walk is bound by instruction dispatch",
+            "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "traffic": 3.716e9 if (n == N_BH and world == 1 and precision == "f64" and args.ratio == 10.0 and not args.opt) else None,
+            "traffic_note": "`traffic` (when filled in) is dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                            "of this very launch (profiles/r2_ncu_bh_walk_group_n4m.csv: N = 4M, ratio 10, one GPU, FP64): 0.1 % "
+                            "of the HBM peak, L2 hit rate 99 % -- the walk is bound by instruction dispatch, not by memory",
+            "traffic_source": "profiles/r2_ncu_bh_walk_group_n4m.csv" if (n == N_BH and world == 1 and precision == "f64" and args.ratio == 10.0 and not args.opt) else None,
             "lane_use": (inter / world) / (32.0 * entries) if entries else None,
             "frac_issued": (32.0 * entries * slots / (force_ms * 1e-3)) / fma_peak if (entries and fma_peak) else None,
             "kernel": "Barnes-Hut walk (all walk launches of one fcompute)", "kernel_ms": force_ms, "phases_ms": r["phases"],

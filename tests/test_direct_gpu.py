@@ -306,3 +306,27 @@ def test_direct_symmetric_tiles_fp32(oracle32, oracle64, n, tile, shape):
     assert np.array_equal(f[:3 * n], y[3 * n:])
     assert rel_err_per_body(f, ref32, n) <= TOL32
     assert rel_err_per_body(f, truth, n) <= max(2 * rel_err_per_body(ref32, truth, n), 2e-6)
+
+
+@pytest.mark.parametrize("shape", [0, 1])
+def test_direct_symmetric_tiles_redo_a_tile_with_the_clamp(oracle64, shape):
+    """The symmetric tiles' first pass leaves out max(r^2, MinDistance) and watches for pairs closer than 1e-4; a tile
+    that holds one is redone with the clamp (diagonal tiles clamp from the start: every body meets itself there).
+    Bodies placed 1e-6 apart and exactly on top of each other, in the SAME tile and in DIFFERENT tiles: the result is
+    the reference's (nbody_data::force, nbody_data.cpp:39-42) for them and for everybody else."""
+    n, tile = 8192, 1024
+    rng = np.random.RandomState(7)
+    pos = rng.uniform(-50, 50, (3, n))
+    vel = rng.uniform(-1, 1, (3, n))
+    m = rng.uniform(0.1, 1.0, n)
+    close = [(10, 5000, 1e-6), (20, 7000, 0.0), (3000, 3001, 1e-6), (4100, 4200, 0.0), (100, 8191, 3e-5)]
+    for i, j, gap in close:
+        pos[:, j] = pos[:, i]
+        pos[0, j] += gap
+    y = np.concatenate([pos.reshape(-1), vel.reshape(-1)])
+    want = oracle64.fcompute_openmp(y, m)
+    f = run_direct(y, m, options=(("direct_symmetric", 1), ("direct_sym_tile", tile), ("direct_sym_shape", shape)))
+    assert np.isfinite(f).all()
+    assert rel_err_per_body(f, want, n) <= TOL64
+    g = run_direct(y, m, options=(("direct_symmetric", 0),))          # ordered-pair kernel: same answer
+    assert rel_err_per_body(f, g, n) <= TOL64
