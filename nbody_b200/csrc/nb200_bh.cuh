@@ -418,7 +418,7 @@ __device__ __forceinline__ void node_force_from_test(real dx, real dy, real dz, 
 	az = fma(-dz, c, az);
 #else
 	const float	r2 = fmaxf(d2, NB200_MIN_DISTANCE);
-	float	yv = rsqrtf(r2);
+	float	yv = nb200_rsqrt_normal(r2);
 	float	c = (yv * yv) * (m * yv);
 	ax = fmaf(-dx, c, ax);
 	ay = fmaf(-dy, c, ay);

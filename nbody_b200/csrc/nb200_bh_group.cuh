@@ -121,7 +121,7 @@ __device__ __forceinline__ void bhg_force(real dx, real dy, real dz, real m, uns
 	const double c = fma(g, u, g);
 #else
 	if(CLAMP) { d2 = fmaxf(d2, NB200_MIN_DISTANCE); }
-	const float yv = mine != 0 ? rsqrtf(d2) : 0.0f;
+	const float yv = mine != 0 ? nb200_rsqrt_normal(d2) : 0.0f;
 	const float c = (yv * yv) * (m * yv);
 #endif
 	ax = fma(-dx, c, ax);

@@ -26,6 +26,18 @@ struct alignas(32) body4 { double x, y, z, m; };
 
 // nbody::MinDistance (nbody/nbtype.h:78): r^2 is clamped to this value.
 
+#ifdef __CUDACC__
+// 1/sqrt(x) for x known to be a normal number (every call site has clamped r^2 to MinDistance = 1e-8 first): the bare
+// MUFU.RSQ. rsqrtf() wraps the same instruction in a denormal-input rescue (FSETP + two predicated FMUL: 4 issue slots
+// instead of 1) that can never trigger here; for normal inputs the results are identical.
+__device__ __forceinline__ float nb200_rsqrt_normal(float x)
+{
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+#endif
+
 #define NB200_MAX_TERMS 48  // fused fmaddn terms per launch (rkfeagin14 needs 35)
 
 struct nb200_terms

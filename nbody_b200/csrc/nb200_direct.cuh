@@ -190,7 +190,7 @@ __device__ __forceinline__ void pair_interaction(float xi, float yi, float zi, c
 	float	dz = s.z - zi;
 	float	r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 	r2 = fmaxf(r2, NB200_MIN_DISTANCE);
-	float	y = rsqrtf(r2);		// MUFU.RSQ, <= 2 ulp
+	float	y = nb200_rsqrt_normal(r2);	// MUFU.RSQ, <= 2 ulp (r2 >= 1e-8: clamped above)
 	float	c = (y * y) * (s.m * y);
 	ax = fmaf(dx, c, ax);
 	ay = fmaf(dy, c, ay);

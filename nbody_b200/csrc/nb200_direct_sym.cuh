@@ -110,7 +110,7 @@ __device__ __forceinline__ void sym_pair(float dx, float dy, float dz, float m_r
 {
 	(void)low;
 	float	r2 = fmaxf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), NB200_MIN_DISTANCE);
-	float	y = rsqrtf(r2);
+	float	y = nb200_rsqrt_normal(r2);
 	float	y3 = (y * y) * y;
 	float	ca = m_col * y3;
 	float	cb = m_row * y3;
@@ -406,7 +406,7 @@ direct_sym_tiles_f32x2(const body4* __restrict__ src, const int2* __restrict__ t
 					f32x2	r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
 					float	r2l, r2h;
 					f2_unpack(r2, r2l, r2h);
-					f32x2	y = f2_pack(rsqrtf(fmaxf(r2l, NB200_MIN_DISTANCE)), rsqrtf(fmaxf(r2h, NB200_MIN_DISTANCE)));
+					f32x2	y = f2_pack(nb200_rsqrt_normal(fmaxf(r2l, NB200_MIN_DISTANCE)), nb200_rsqrt_normal(fmaxf(r2h, NB200_MIN_DISTANCE)));
 					f32x2	y3 = f2_mul(f2_mul(y, y), y);
 					f32x2	ca = f2_mul(mb, y3);
 					f32x2	ncb = f2_mul(nma[k], y3);

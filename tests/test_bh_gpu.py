@@ -261,3 +261,26 @@ def test_bh_c4_n4m_ratio10_sampled(oracle64):
     got = f.reshape(6, n)[3:, bodies]
     assert rel_err_per_body(got, want, bodies.size) <= TOL
     assert np.array_equal(f[:3 * n], y[3 * n:])
+
+
+def test_bh_walk_profile_counters_are_consistent():
+    """nb200_bh_walk_profile: rounds of at most 32 work items, at most 64 list entries per round, every entry naming at
+    least one target; the entry histogram covers all entries but each group's last round."""
+    from nbody_b200 import Engine
+    y, m = universe(65536)
+    with Engine(kind="bh", distance_to_node_radius_ratio=10.0) as e:
+        assert e.init(y, m)
+        f = e.create_buffer(e.get_y().size())
+        e.bh_walk_stats(True)
+        e.fcompute(0.0, e.get_y(), f)
+        e.synchronize()
+        p = e.bh_walk_profile()
+        visits, inter = e.bh_walk_stats(False)
+    groups = 65536 // 32
+    assert 0 < p["items"] <= 32 * p["rounds"] and p["entries"] <= 64 * p["rounds"] + groups
+    assert visits == 2 * 0 + visits and visits >= 2 * p["items"]            # every item is two node visits by >= 1 target
+    assert p["entries"] <= inter <= 32 * p["entries"]
+    hist = sum(p[k] for k in ("entries_32", "entries_24_31", "entries_16_23", "entries_8_15", "entries_1_7"))
+    assert p["entries"] - 64 * groups <= hist <= p["entries"]
+    assert p["busiest_target_entries"] <= p["entries"] and p["busiest_target_entries_whole_walk"] * 32 >= inter * 0.9
+    assert 0 < p["max_stack"] <= 512 and p["unsure_lane_items"] < p["items"] // 100

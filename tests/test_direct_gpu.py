@@ -330,3 +330,24 @@ def test_direct_symmetric_tiles_redo_a_tile_with_the_clamp(oracle64, shape):
     assert rel_err_per_body(f, want, n) <= TOL64
     g = run_direct(y, m, options=(("direct_symmetric", 0),))          # ordered-pair kernel: same answer
     assert rel_err_per_body(f, g, n) <= TOL64
+
+
+def test_use_nccl_needs_distinct_devices_and_otherwise_changes_nothing(oracle64):
+    """use_nccl=1 (the reference's factory parameter): one lane has nothing to exchange; a device list that repeats a
+    device cannot form NCCL communicators -- the option is refused, the peer path stays, results are unchanged."""
+    from nbody_b200 import Engine
+    g = load_golden_npz("g1_n2048")
+    want = oracle64.fcompute_openmp(g["y"], g["mass"])
+    with Engine(devices="0") as e:
+        assert e.set_option("use_nccl", 1) == 0
+        assert e.init(g["y"], g["mass"])
+        f = e.create_buffer(e.get_y().size())
+        e.fcompute(0.0, e.get_y(), f)
+        assert rel_err_per_body(e.read_buffer(f), want, 2048) <= TOL64
+    with Engine(devices="0,0") as e:
+        assert e.set_option("use_nccl", 1) != 0 and "repeats device" in e.last_error()
+        assert e.init(g["y"], g["mass"])
+        f = e.create_buffer(e.get_y().size())
+        e.fcompute(0.0, e.get_y(), f)
+        assert rel_err_per_body(e.read_buffer(f), want, 2048) <= TOL64
+        assert "peer" in e.print_info()
