@@ -204,7 +204,11 @@ __device__ __forceinline__ int sym_tile(const body4* __restrict__ src, const int
 					nxt[q] = cols[bblk * 32 * J + q * 32 + lane];
 				}
 			}
-#pragma unroll 1
+#ifndef NB200_SYM_STEP_UNROLL
+#define NB200_SYM_STEP_UNROLL 1
+#endif
+			constexpr int step_unroll = NB200_SYM_STEP_UNROLL;
+#pragma unroll step_unroll
 			for(int step = 0; step < 32; ++step)
 			{
 				// column body q moves on as soon as its I pairs are done, while the pairs of column body q + 1 (and, across
