@@ -643,7 +643,7 @@ nbody_engine* nbody_create_engine_b200(const QVariantMap& param)
 	{
 		nbcoord_t	ratio = param.value("distance_to_node_radius_ratio", 10).toDouble();
 		size_t		tree_build_rate = param.value("tree_build_rate", 0).toULongLong();
-		QString		strtl(param.value("tree_layout", "heap_stackless").toString());
+		QString		strtl(param.value("tree_layout", "heap").toString());	// the cuda_bh_tex default (nbody_engines.cpp:64)
 		e_tree_layout tl = tree_layout_from_str(strtl);
 		if(tl != etl_heap && tl != etl_heap_stackless)
 		{

@@ -1,5 +1,6 @@
 import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 os.environ['NBREF_QUIET']='1'
 import numpy as np
 from nbody_b200 import Engine
@@ -35,7 +36,7 @@ with Engine(kind="bh") as e:
     f = e.create_buffer(e.get_y().size())
     e.fcompute(0, e.get_y(), f)
     print("bh4096", e.fmaxabs(f))
-for mode in (0, 4, 32):                # walk variants: two / four / one target(s) per lane
+for mode in (0, 2, 4, 32):             # walk variants: grouped (default) / two / four / one target(s) per lane
     with Engine(kind="bh") as e:
         e.set_option("walk_mode", mode)
         assert e.init(y, m)
@@ -74,3 +75,36 @@ with Engine() as e:                    # step table: two alternating steps, both
         e.fmadd_inplace(e.get_y(), dy, 1e-3 if i % 2 else 5e-4)
         e.advise_time(1e-3)
     print("alternating steps", e.step_graph_stats(), e.fmaxabs(e.get_y()))
+
+# round 2: grouped walk with counters (STATS instantiation) and in the FP32 build; several shards; a lattice with
+# knife-edge cells (the FP64 re-evaluation path); symmetric tiles whose first pass meets close pairs (clamp redo)
+n = 4096
+y = rng.uniform(-50, 50, 6*n); m = rng.uniform(0.1, 2, n)
+for prec, dev in (("f64", "0"), ("f32", "0"), ("f64", "0,0,0,0")):
+    with Engine(kind="bh", precision=prec, devices=dev) as e:
+        assert e.init(y, m)
+        f = e.create_buffer(e.get_y().size())
+        e.bh_walk_stats(True)
+        e.fcompute(0, e.get_y(), f)
+        print("grouped walk", prec, dev, e.bh_walk_stats(False), e.bh_walk_profile()["max_stack"], e.fmaxabs(f))
+g = np.arange(16, dtype=np.float64)
+pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+yl = np.concatenate([pos[:, 0], pos[:, 1], pos[:, 2], np.zeros(3 * 4096)])
+with Engine(kind="bh", distance_to_node_radius_ratio=2.0) as e:
+    assert e.init(yl, np.ones(4096))
+    f = e.create_buffer(e.get_y().size())
+    e.bh_walk_stats(True)
+    e.fcompute(0, e.get_y(), f)
+    print("lattice", e.bh_walk_profile()["unsure_lane_items"], e.fmaxabs(f))
+n = 4096
+y = rng.uniform(-50, 50, 6*n); m = rng.uniform(0.1, 2, n)
+yy = y.reshape(6, n)
+yy[0:3, 3000] = yy[0:3, 10]; yy[0, 3000] += 1e-6      # a close pair across tiles, and a coincident one
+yy[0:3, 2000] = yy[0:3, 20]
+for shape in (0, 1):
+    with Engine() as e:
+        e.set_option("direct_symmetric", 1); e.set_option("direct_sym_tile", 512); e.set_option("direct_sym_shape", shape)
+        assert e.init(yy.reshape(-1), m)
+        f = e.create_buffer(e.get_y().size())
+        e.fcompute(0, e.get_y(), f)
+        print("sym redo shape", shape, e.last_direct_path(), e.fmaxabs(f))
