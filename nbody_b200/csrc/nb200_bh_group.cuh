@@ -2,18 +2,19 @@
 //
 // The warp-coherent walks of nb200_bh.cuh keep the reference's shape -- one traversal state per target -- and pay the
 // bookkeeping of a visit (node load, skip_idx algebra, votes, loop control: ~45 issue slots) once per node and warp
-// for 8..16 slots of useful arithmetic. Here a warp owns a GROUP of 32 consecutive leaves and alternates two phases:
+// for 16 slots of acceptance arithmetic. Here a warp owns a GROUP of 32 consecutive leaves and works in rounds:
 //
 //   decide  A work item is (parent p, mask M): "the targets in M opened p, so its children 2p and 2p+1 are theirs to
 //           test". Each LANE takes one item off the warp's stack in shared memory, loads the sibling pair (64
-//           contiguous bytes) and tests it against all 32 targets of the group (positions broadcast from shared
-//           memory, two targets per packed f32x2 instruction). The result is one accept word and one open word per
-//           child: accepted (node, mask) pairs are appended to the warp's interaction list, opened internal children
-//           become new items. Bookkeeping is per lane and per item, i.e. amortised over 64 acceptance tests, and 32
-//           items are in flight per warp instead of one node.
-//   sum     When the list fills up (and at the end) the warp switches to one target per lane and runs down the list:
-//           one broadcast load per accepted node, the lanes named in its mask add the node's attraction in nbcoord_t
-//           -- the same expression, term by term, as the other walks and the reference (node_force_from_test).
+//           contiguous bytes, and the two masses) and tests it against all 32 targets of the group (positions
+//           broadcast from shared memory, two targets per packed f32x2 instruction). The result is one accept word and
+//           one open word per child: accepted nodes go to the warp's interaction list TOGETHER WITH THEIR DATA
+//           (mass centre, mass, target mask), opened internal children become new items. Bookkeeping is per lane and
+//           per item, i.e. amortised over 64 acceptance tests, and 32 items are in flight per warp instead of one node.
+//   sum     Between the node loads of a round and its tests -- i.e. while those loads are in flight -- the warp
+//           switches to one target per lane and runs down the list of the PREVIOUS round (at most 64 entries, read
+//           from shared memory only, one broadcast per entry): the lanes named in an entry's mask add the node's
+//           attraction in nbcoord_t with the formulas of node_force_from_test; the others add exactly +-0 (no branch).
 //
 // Which nodes a target accepts is decided exactly as in nbody_space_heap_stackless::traverse
 // (nbody_space_heap_stackless.cpp:3-28): d2 > radius_sqr on the node, else its children. What changes is only the
@@ -21,16 +22,19 @@
 // agree with the other walks to rounding (~1e-15 relative, tested <= 1e-13), not bit for bit; they are still a pure
 // function of the inputs (no atomics, no scheduling dependence) and identical for every shard count.
 //
-// FP64 build -- certified FP32 decisions. The 3.6e11 acceptance tests of an N = 4M walk would cost as many FP64-pipe
+// FP64 build -- certified FP32 decisions. The 4.1e11 acceptance tests of an N = 4M walk would cost as many FP64-pipe
 // slots as the force sums themselves. Each test is therefore evaluated in FP32 on coordinates RELATIVE to the group's
 // first target (the subtraction is done in FP64 once per node and lane, then rounded), which makes the error of
-// t = d2 - radius_sqr a few ulp of d2: with u = 2^-24, R = the group's extent, |t_fp32 - t_exact| <= u (18.5 w + 3.5 R^2)
+// t = d2 - radius_sqr a few ulp of d2: with u = 2^-24, R = the group's extent, |t_fp32 - t_exact| <= u (17.4 w + 3.5 R^2)
 // at the decision boundary d2 = w (derivation in DESIGN.md 3.4). A test with |t| > m = 32 u (w + R^2) is therefore
-// decided by the sign of t; anything closer to the boundary (about 1e-5 of all tests) is re-evaluated by the lane in
-// FP64 with the reference's own expression. Visit and interaction counts equal the oracle's (tested), knife-edge
-// cells included.
+// decided by the sign of t; anything closer to the boundary (4e-4 of the lane-items) is re-evaluated by the lane in
+// FP64 with the reference's own expression (bh_d2). Visit and interaction counts equal the oracle's (tested),
+// knife-edge cells included.
 // FP32 build: the reference's own arithmetic is FP32, so the packed tests ARE the reference expression
 // (fma(dz,dz,fma(dx,dx,dy*dy)) > w on absolute coordinates) and need no certificate.
+//
+// Cost model: an FP64 instruction holds the dispatch port for two cycles, anything else for one. Per
+// round: decide 417 instructions, sum 39 entries x (16 FP64 + 7.6 others). N = 4M, ratio 10, one B200: 393 ms.
 #ifndef NB200_BH_GROUP_CUH
 #define NB200_BH_GROUP_CUH
 
