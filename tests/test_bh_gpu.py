@@ -284,3 +284,29 @@ def test_bh_walk_profile_counters_are_consistent():
     assert p["entries"] - 64 * groups <= hist <= p["entries"]
     assert p["busiest_target_entries"] <= p["entries"] and p["busiest_target_entries_whole_walk"] * 32 >= inter * 0.9
     assert 0 < p["max_stack"] <= 512 and p["unsure_lane_items"] < p["items"] // 100
+
+
+def test_bh_beyond_the_headline_size_and_a_tiny_stack_budget():
+    """N = 8,388,608 (one level deeper than C4), ratio 4: the grouped walk against the two-targets-per-lane walk, whose
+    order of summation is the reference's -- equal node-visit and interaction counts, forces to rounding -- and the
+    item stack stays well inside its 512 slots (above 448 the walk would fall back to one item at a time)."""
+    from nbody_b200 import Engine
+    n = 1 << 23
+    y, m = universe(n)
+    out = {}
+    for mode in (2, 0):
+        with Engine(kind="bh", distance_to_node_radius_ratio=4.0) as e:
+            e.set_option("walk_mode", mode)
+            assert e.init(y, m)
+            f = e.create_buffer(e.get_y().size())
+            e.bh_walk_stats(True)
+            e.fcompute(0.0, e.get_y(), f)
+            e.synchronize()
+            prof = e.bh_walk_profile() if mode == 0 else None
+            out[mode] = (e.read_buffer(f), e.bh_walk_stats(False), prof)
+    assert out[0][1] == out[2][1] and out[0][1][0] > out[0][1][1] > 0
+    # two orders of summation over ~1e4 terms per target: equal to rounding. Among 8M bodies a few have attractions that
+    # nearly cancel, which amplifies the relative figure; measured against the typical size of an acceleration it is 1e-13
+    assert rel_err_per_body(out[0][0], out[2][0], n) <= 1e-12
+    assert rel_err_per_body(out[0][0], out[2][0], n, floor=1e-2) <= 1e-13
+    assert 0 < out[0][2]["max_stack"] < 448
