@@ -30,7 +30,8 @@
  * rank `rank` of `nranks` processes; total shards G = nlanes * nranks (one of
  * the two factors must be 1). A buffer whose size is exactly 6*N*sizeof(real)
  * (a state vector) is BODY-SHARDED: shard g holds columns [g*N/G, (g+1)*N/G)
- * of every row. Any other buffer is replicated on every shard. Host-facing
+ * of every row (a buffer of that size created before nb200_set_bodies becomes
+ * one at that call, contents preserved). Any other buffer is replicated on every shard. Host-facing
  * calls (nb200_write / nb200_read) always take and return the full logical
  * buffer, so callers never see the sharding. With nranks > 1 every rank makes
  * the same sequence of calls (SPMD); fcompute all-gathers packed source bodies

@@ -529,14 +529,37 @@ NB200_API int nb200_set_bodies(nb200_ctx* ctx, size_t n, const nb200_real* mass)
 	ctx->n = n;
 	ctx->sym_unavailable = false;
 	ctx->n_shard = n / static_cast<size_t>(ctx->nshards);
-	if(ctx->nshards == 1)
+	// A state-sized buffer created BEFORE the body count was known (the adapter allows create_buffer before init) was
+	// laid out as a replicated buffer. One shard: that is the layout of a state vector anyway. Several shards: every lane
+	// holds the whole vector and keeps only its own columns from here on (contents preserved).
+	for(const nb200_buf* cb : ctx->live)
 	{
-		// one shard: a state-sized buffer created before the body count was known has the layout of a state vector anyway
-		for(const nb200_buf* cb : ctx->live)
+		nb200_buf* b = const_cast<nb200_buf*>(cb);
+		if(b->bytes != 6 * n * sizeof(real) || b->sharded) { continue; }
+		if(ctx->nshards > 1)
 		{
-			nb200_buf* b = const_cast<nb200_buf*>(cb);
-			b->sharded = b->bytes == 6 * n * sizeof(real);
+			const size_t n_shard = n / static_cast<size_t>(ctx->nshards);
+			for(size_t i = 0; i < ctx->lanes.size(); ++i)
+			{
+				nb200_lane& l = ctx->lanes[i];
+				CU(ctx, cudaSetDevice(l.dev));
+				void* shard = nullptr;
+				if(cudaMalloc(&shard, 6 * n_shard * sizeof(real)) != cudaSuccess)
+				{
+					cudaGetLastError();
+					return fail(ctx, NB200_ERR_ALLOC, "set_bodies: re-sharding an early state vector failed");
+				}
+				const char* from = static_cast<const char*>(b->dptr[i]) + static_cast<size_t>(l.shard) * n_shard * sizeof(real);
+				CU(ctx, cudaMemcpy2DAsync(shard, n_shard * sizeof(real), from, n * sizeof(real), n_shard * sizeof(real), 6,
+										  cudaMemcpyDeviceToDevice, l.stream));
+				CU(ctx, cudaStreamSynchronize(l.stream));
+				cudaFree(b->dptr[i]);
+				b->dptr[i] = shard;
+			}
+			b->lane_elems = 6 * n_shard;
+			b->lane_bytes = b->lane_elems * sizeof(real);
 		}
+		b->sharded = true;
 	}
 	ctx->n_pad = (n + NB200_DIRECT_TILE - 1) / NB200_DIRECT_TILE * NB200_DIRECT_TILE;
 	ctx->n_alloc = (n + 8191) / 8192 * 8192 + 8192;	// room for the zero-mass padding of a last tile of any edge <= 8192

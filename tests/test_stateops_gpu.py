@@ -325,14 +325,19 @@ def test_fmaxabs_nan_follows_the_reference_loop(ref64, devices):
     d.close()
 
 
-def test_state_sized_buffer_created_before_the_bodies_are_known():
-    """One shard: a buffer of 6N reals allocated before set_bodies / init has the layout of a state vector and is
-    accepted as one afterwards (the adapter allows create_buffer before init)."""
+@pytest.mark.parametrize("devices", ["0", "0,0", "0,0,0,0"])
+def test_state_sized_buffer_created_before_the_bodies_are_known(devices):
+    """A buffer of 6N reals allocated before set_bodies / init (the adapter allows create_buffer before init) is a
+    state vector afterwards: with one shard it already has that layout, with several each lane keeps its own columns
+    of what was written into it."""
     from nbody_b200 import Engine
     g = load_golden_npz("g1_n128")
-    with Engine() as e:
+    with Engine(devices=devices) as e:
         early = e.create_buffer(6 * 128 * 8)
+        marks = np.arange(6 * 128, dtype=np.float64)
+        e.write_buffer(early, marks)
         assert e.init(g["y"], g["mass"])
+        assert np.array_equal(e.read_buffer(early), marks)          # contents survive the re-sharding
         e.fcompute(0.0, e.get_y(), early)
         late = e.create_buffer(6 * 128 * 8)
         e.fcompute(0.0, e.get_y(), late)
