@@ -1,3 +1,4 @@
+# N ranks on one node: tests/mp_check.py (parity of the sharded paths) and the bench line; usage: bash profiles/run_multi_gpu.sh N [nocheck]
 N=${1:-2}
 if [ "$2" != "nocheck" ]; then
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 tests/mp_check.py > gpurun_out/r2_mp_check_${N}gpu.log 2>&1; grep "mp_check\|rank . done\|Error\|error" gpurun_out/r2_mp_check_${N}gpu.log | tail -8
