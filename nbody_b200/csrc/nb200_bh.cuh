@@ -20,15 +20,18 @@
 //           choice there is whatever std::nth_element happens to do.
 //   update  leaves, then one launch per level bottom-up (kupdate_node_bh_tex,
 //           nbody_engine_cuda_impl.cu:644-714), top 256 nodes in one CTA.
-//   walk    warp-coherent stackless walk (default): the 32 targets of a warp are consecutive
+//   walk    default: the grouped walk of nb200_bh_group.cuh (a warp per 32 consecutive leaves; lanes work on nodes while
+//           deciding, on targets while summing). This file holds the walks that keep one traversal state per target
+//           (walk_mode 32 / 2 / 4 / 1) -- the form whose summation order is the reference's:
+//           warp-coherent stackless walk: the 32 targets of a warp are consecutive
 //           leaves (a compact cell of the kd-order), the warp walks the UNION of their
 //           traversals with a warp-uniform `curr`, so each node is one broadcast load instead
 //           of 32 divergent ones. A lane that accepts a node sleeps until curr reaches that
 //           node's skip_idx; every lane therefore accepts exactly the nodes, in exactly the
 //           order, of its own nbody_space_heap_stackless::traverse
 //           (nbody_space_heap_stackless.cpp:3-28) -- results are bit-identical to the
-//           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape). By default each lane
-//           carries TWO targets (bh_walk_warp_multi<2>: the warp walks the union of 64 consecutive leaves), which
+//           per-thread walk (walk_mode 1, the reference's kfcompute_heap_bh_stackless shape). bh_walk_warp_multi<2>
+//           lets each lane carry TWO targets (the warp walks the union of 64 consecutive leaves), which
 //           shares the node load, index algebra, votes and loop control of a visit between two acceptance tests.
 //
 //   shards  with G shards (lanes or ranks) every shard builds the whole tree and walks chunks of 4096 CONSECUTIVE
@@ -893,7 +896,7 @@ static int bh_fcompute(nb200_ctx* ctx, nb200_lane& l, const real* y, real* f, si
 	else if(ctx->opt_walk_mode != 32)
 	{
 		// several targets per lane (a deal chunk is a multiple of 128 leaves or the whole shard, so a warp's leaves stay
-		// consecutive). Two is the measured optimum and the default: N = 4M, ratio 10 on one B200 -- FP64 675 -> 600 ms,
+		// consecutive). Two is the measured optimum of this family (round 1's default): N = 4M, ratio 10 on one B200 -- FP64 675 -> 600 ms,
 		// FP32 647 -> 438 ms; four: 754 / 439 ms (114 registers, a quarter of the warp slots)
 		const int		tpl = ctx->opt_walk_mode == 4 ? 4 : 2;
 		const unsigned	mgrid = static_cast<unsigned>((n_targets + 128 * tpl - 1) / (128 * tpl));
