@@ -544,36 +544,39 @@ void nbody_engine_b200::print_info() const
 
 int nbody_engine_b200::select_devices(const QString& devices_str)
 {
-	QStringList	dev_list(devices_str.split(",", QString::SkipEmptyParts));
-	if(dev_list.isEmpty())
-	{
-		qDebug() << "CUDA device list is empty";
-		return -1;
-	}
-	int	device_count = 0;
-	if(nb200_device_count(&device_count) != NB200_OK || device_count <= 0)
+	// Contract of nbody_engine_cuda::select_devices (nbody_engine_cuda.cpp:576-616): a comma list of device ordinals,
+	// every one of them present; 0 on success, anything else leaves the engine's device list untouched.
+	int	present = 0;
+	if(nb200_device_count(&present) != NB200_OK || present <= 0)
 	{
 		qDebug() << "No CUDA devices found";
 		return -1;
 	}
-	std::vector<int>	device_ids;
-	for(int i = 0; i != dev_list.size(); ++i)
+	const QStringList	fields(devices_str.split(",", QString::SkipEmptyParts));
+	std::vector<int>	chosen;
+	chosen.reserve(static_cast<size_t>(fields.size()));
+	for(int k = 0; k != fields.size(); ++k)
 	{
-		bool	ok = false;
-		int		dev_id = dev_list[i].toInt(&ok);
-		if(!ok)
+		bool		is_number = false;
+		const int	ordinal = fields[k].toInt(&is_number);
+		if(!is_number)
 		{
-			qDebug() << "Can't parse device ID" << dev_list[i];
+			qDebug() << "Can't parse device ID" << fields[k];
 			return -1;
 		}
-		if(dev_id < 0 || dev_id >= device_count)
+		if(ordinal < 0 || ordinal >= present)
 		{
-			qDebug() << "Invalid device ID" << dev_id << "must be in range [0 ..." << device_count << ")";
+			qDebug() << "Invalid device ID" << ordinal << "must be in range [0 ..." << present << ")";
 			return -1;
 		}
-		device_ids.push_back(dev_id);
+		chosen.push_back(ordinal);
 	}
-	d->m_device_ids = device_ids;
+	if(chosen.empty())
+	{
+		qDebug() << "CUDA device list is empty";
+		return -1;
+	}
+	d->m_device_ids.swap(chosen);
 	return 0;
 }
 
