@@ -921,7 +921,9 @@ int sym_tile_edge(const nb200_ctx* ctx)
 	if(ctx->opt_direct_sym == 0 || ctx->sym_unavailable) { return 0; }
 	if(ctx->lanes.size() > 1 && !ctx->lanes_nccl && (ctx->nranks > 1 || !ctx->peer_loads || ctx->lanes.size() > NB200_SYM_MAX_PEERS)) { return 0; }
 	if(ctx->opt_direct_sym < 0 && ctx->n < NB200_SYM_MIN_BODIES) { return 0; }	// too few tiles to fill 148 SMs
-	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(3) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }	// partials > ~30 GB per rank
+	// tile partials are 24 N^2 / T bytes over all ranks: 51 GB at N = 4M, 80 GB at 5M (a B200 has 180 GB); if they do not fit
+	// next to the caller's buffers every shard falls back together (sym_fcompute)
+	if(ctx->opt_direct_sym < 0 && ctx->n > (static_cast<size_t>(5) << 20) * static_cast<size_t>(ctx->nranks)) { return 0; }
 	// automatic edge: ~N/128 (>= 8000 equal tiles for N >= 32,768), at most 8192 (192 KB of column sums; scratch
 	// 24 N^2 / T bytes), at least 256 (the default kernels then run 2-warp / 1-warp CTAs, several per SM)
 	long long edge = ctx->opt_sym_tile;

@@ -174,6 +174,26 @@ def test_direct_c3_n1m_sampled_and_momentum(oracle64):
     assert np.all(np.abs(force) <= 1e-10 * scale)
 
 
+def test_direct_n4m_uses_the_symmetric_tiles_and_stays_exact(oracle64):
+    """Four times BASELINE's C3: N = 4,194,304 (1.76e13 pairs, 51 GB of tile partials on the 180 GB part) still takes
+    the symmetric tiles; 24 sampled bodies vs the oracle and Newton's third law over all of them."""
+    from nbody_b200 import Engine
+    n = 1 << 22
+    y, m = universe(n)
+    with Engine() as e:
+        assert e.init(y, m)
+        fb = e.create_buffer(e.get_y().size())
+        e.fcompute(0.0, e.get_y(), fb)
+        f = e.read_buffer(fb).reshape(6, n)
+        assert e.last_direct_path() == 8192
+    t = np.unique(np.concatenate([[0, n // 2], np.random.RandomState(6).randint(0, n, 22)]))
+    ref = oracle64.accel_subset(y, m, t)
+    assert rel_err_per_body(f[3:, t], ref, t.size) <= TOL64
+    force = (f[3:] * m[None, :]).sum(axis=1)
+    scale = np.abs(f[3:] * m[None, :]).sum(axis=1)
+    assert np.all(np.abs(force) <= 1e-10 * scale)
+
+
 def test_multi_process_nccl_two_ranks():
     """One process per GPU over NCCL (skipped on a single-GPU box; the gloo tests cover the host logic there)."""
     import os
