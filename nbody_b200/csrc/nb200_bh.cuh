@@ -74,6 +74,7 @@ struct bh_state
 	int*	ord[3] = {nullptr, nullptr, nullptr};
 	int*	ord_tmp[3] = {nullptr, nullptr, nullptr};
 	unsigned char*	side = nullptr;
+	unsigned char*	side_next = nullptr;	// written by a level's scatter pass for the level below
 	unsigned*	blk = nullptr;	// [3][n / PART_BLOCK + 1]
 	void*	cub_tmp = nullptr;
 	size_t	cub_bytes = 0;
@@ -98,7 +99,7 @@ static void bh_free(bh_state* s)
 {
 	if(s == nullptr) { return; }
 	void* ptrs[] = {s->xyzr, s->nmass, s->bmin, s->bmax, s->body_n, s->keys_in, s->keys_out, s->iota, s->ord[0], s->ord[1],
-					s->ord[2], s->ord_tmp[0], s->ord_tmp[1], s->ord_tmp[2], s->side, s->blk, s->cub_tmp, s->leaf_pos,
+					s->ord[2], s->ord_tmp[0], s->ord_tmp[1], s->ord_tmp[2], s->side, s->side_next, s->blk, s->cub_tmp, s->leaf_pos,
 					s->acc_all, s->lpt_cost, s->lpt_cost_sorted, s->lpt_iota, s->lpt_order, s->lpt_tmp};
 	for(void* p : ptrs)
 	{
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(1024) bh_part_scan(unsigned* __restrict__ blk,
 __global__ void __launch_bounds__(256) bh_part_scatter(const int* __restrict__ o0, const int* __restrict__ o1,
 														int* __restrict__ d0, int* __restrict__ d1,
 														const unsigned char* __restrict__ side, const unsigned* __restrict__ blk,
-														int nblk, int seg)
+														int nblk, int seg, unsigned char* __restrict__ side_next)
 {
 	const int*	ord = blockIdx.y == 0 ? o0 : o1;
 	int*		dst = blockIdx.y == 0 ? d0 : d1;
@@ -205,6 +206,13 @@ __global__ void __launch_bounds__(256) bh_part_scatter(const int* __restrict__ o
 								: s0 + (seg >> 1) + (i - s0) - static_cast<int>(in_seg_left);
 		dst[d] = body[q];
 		before += left[q];
+		// ordering 0 of this pass is the one the NEXT level splits along: its bodies' new positions say on which side of
+		// the next median they fall, so the next level needs no bh_mark_side pass of its own
+		if(side_next != nullptr && blockIdx.y == 0)
+		{
+			const int half = seg >> 1;	// the next level's segment size
+			side_next[body[q]] = ((d & (half - 1)) >= (half >> 1)) ? 1 : 0;
+		}
 	}
 }
 
@@ -683,6 +691,7 @@ static int bh_alloc(nb200_ctx* ctx, nb200_lane& l, std::string& err)
 	{
 		ok = cudaMalloc(&s->keys_in, n * sizeof(real)) == cudaSuccess && cudaMalloc(&s->keys_out, n * sizeof(real)) == cudaSuccess &&
 			 cudaMalloc(&s->iota, n * sizeof(int)) == cudaSuccess && cudaMalloc(&s->side, n) == cudaSuccess &&
+			 cudaMalloc(&s->side_next, n) == cudaSuccess &&
 			 cudaMalloc(&s->blk, 3 * nblk * sizeof(unsigned)) == cudaSuccess;
 		for(int a = 0; a < 3 && ok; ++a)
 		{
@@ -746,13 +755,21 @@ static int bh_build_topology(nb200_ctx* ctx, nb200_lane& l, int& launches, std::
 	for(int seg = n; seg > NB200_BH_LOCAL; seg >>= 1, ++depth)
 	{
 		const int c = depth % 3, a0 = (c + 1) % 3, a1 = (c + 2) % 3;
-		bh_mark_side<<<g256, 256, 0, l.stream>>>(s->ord[c], s->side, n, seg);
+		// side flags along the split dimension: level 0 marks them from the presorted ordering; every later level got them
+		// from the scatter pass of the level above (a0 of one level is the split dimension of the next)
+		if(depth == 0)
+		{
+			bh_mark_side<<<g256, 256, 0, l.stream>>>(s->ord[c], s->side, n, seg);
+			++launches;
+		}
+		const bool more = (seg >> 1) > NB200_BH_LOCAL;	// another global level follows
 		// the ordering along the split dimension is already partitioned (its lower half IS the left child)
 		bh_part_count<<<dim3(nblk, 2), 256, 0, l.stream>>>(s->ord[a0], s->ord[a1], s->side, s->blk, nblk);
 		bh_part_scan<<<2, 1024, 0, l.stream>>>(s->blk, nblk);
 		bh_part_scatter<<<dim3(nblk, 2), 256, 0, l.stream>>>(s->ord[a0], s->ord[a1], s->ord_tmp[a0], s->ord_tmp[a1], s->side,
-															   s->blk, nblk, seg);
-		launches += 4;
+															   s->blk, nblk, seg, more ? s->side_next : nullptr);
+		launches += 3;
+		std::swap(s->side, s->side_next);
 		std::swap(s->ord[a0], s->ord_tmp[a0]);
 		std::swap(s->ord[a1], s->ord_tmp[a1]);
 	}
